@@ -1,0 +1,89 @@
+# vkhel-b200 build.  Replaces the reference's meson build (meson.build:31-57):
+# same product shape -- a static libvkhel_priv.a with every symbol (what the
+# reference's tests link, test/meson.build:6,11,16) and a shared libvkhel.so
+# that exports vkhel_* only (vkhel.syms) -- built with nvcc for sm_100a.
+#
+#   make            libraries + oracle + (if /root/reference exists) the
+#                   reference's own example and tests, compiled unmodified
+#   make DEBUG=1    adds -DVKHEL_DEBUG (reference option debug_logging)
+#   make check-host run the host-only reference tests (numbers, ntt)
+#   make check      run all reference programs (needs a GPU)
+
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+REF       ?= /root/reference
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+INC       := -Iinclude -Iinclude/vkhel -Ivkhel_b200/csrc
+DEFS      := $(if $(DEBUG),-DVKHEL_DEBUG,)
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall $(INC) $(DEFS)
+CFLAGS    := -O2 -fPIC -Wall -Wextra $(INC) $(DEFS)
+
+SRC_DIR := vkhel_b200/csrc
+OBJ_DIR := build/obj
+LIB_DIR := vkhel_b200/lib
+BIN_DIR := build/bin
+
+CU_SRCS := $(SRC_DIR)/device.cu $(SRC_DIR)/vector.cu \
+           $(SRC_DIR)/kernels_elem.cu $(SRC_DIR)/kernels_ntt.cu
+C_SRCS  := $(SRC_DIR)/numbers.c $(SRC_DIR)/ntt_tables.c
+OBJS    := $(CU_SRCS:$(SRC_DIR)/%.cu=$(OBJ_DIR)/%.o) \
+           $(C_SRCS:$(SRC_DIR)/%.c=$(OBJ_DIR)/%.o)
+HDRS    := $(wildcard include/vkhel/*.h include/priv/*.h $(SRC_DIR)/*.cuh)
+
+SHARED := $(LIB_DIR)/libvkhel.so
+STATIC := $(LIB_DIR)/libvkhel_priv.a
+
+# link line for a C program against the static library
+CUDA_LIBS := -L/usr/local/cuda/lib64 -lcudart_static -lstdc++ -lpthread -ldl -lrt -lm
+
+REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
+	$(BIN_DIR)/ref_example $(BIN_DIR)/ref_test_vector \
+	$(BIN_DIR)/ref_test_ntt $(BIN_DIR)/ref_test_numbers,)
+
+.PHONY: all libs oracle refbins clean check check-host
+all: libs oracle refbins
+libs: $(SHARED) $(STATIC)
+refbins: $(REF_BINS)
+
+$(OBJ_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
+	@mkdir -p $(OBJ_DIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(OBJ_DIR)/%.o: $(SRC_DIR)/%.c $(HDRS)
+	@mkdir -p $(OBJ_DIR)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(STATIC): $(OBJS)
+	@mkdir -p $(LIB_DIR)
+	rm -f $@
+	ar rcs $@ $^
+
+$(SHARED): $(OBJS) vkhel.syms
+	@mkdir -p $(LIB_DIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) \
+		-Xlinker --version-script=vkhel.syms -Xlinker -soname=libvkhel.so
+
+# ---- the reference's own programs, compiled from where they lie, unmodified ----
+# (include path = include/ and include/vkhel/, as in meson.build:31-32)
+$(BIN_DIR)/ref_example: $(REF)/examples/example.c $(SHARED)
+	@mkdir -p $(BIN_DIR)
+	$(CC) -O2 $(INC) $< -o $@ -L$(LIB_DIR) -lvkhel -Wl,-rpath,'$$ORIGIN/../../$(LIB_DIR)'
+
+$(BIN_DIR)/ref_test_%: $(REF)/test/%.c $(STATIC)
+	@mkdir -p $(BIN_DIR)
+	$(CC) -O2 $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+oracle:
+	$(MAKE) -C oracle REF=$(REF)
+
+check-host: $(BIN_DIR)/ref_test_numbers $(BIN_DIR)/ref_test_ntt
+	$(BIN_DIR)/ref_test_numbers
+	$(BIN_DIR)/ref_test_ntt
+
+check: check-host $(BIN_DIR)/ref_test_vector $(BIN_DIR)/ref_example
+	$(BIN_DIR)/ref_test_vector
+	$(BIN_DIR)/ref_example
+
+clean:
+	rm -rf build $(LIB_DIR)
+	$(MAKE) -C oracle clean

@@ -1,0 +1,47 @@
+/*
+ * CUDA device layer: the replacement for the reference's Vulkan layer
+ * (include/priv/vulkan.h:50-57, src/vulkan.c) and its VMA allocator.
+ * Plain C so that test programs can include priv/vkhel.h without CUDA headers.
+ */
+#ifndef PRIV_DEVICE_H
+#define PRIV_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKHEL_PINNED_SLOTS 8
+
+struct pinned_slot {
+	void *ptr;
+	size_t bytes;
+	int in_use;
+};
+
+struct device_ctx {
+	int device;          /* CUDA ordinal */
+	int sm_count;
+	size_t smem_optin;   /* max dynamic shared memory per block */
+	size_t l2_bytes;
+	void *stream;        /* cudaStream_t */
+	void *mem_pool;      /* cudaMemPool_t: stream-ordered allocator */
+	struct pinned_slot pinned[VKHEL_PINNED_SLOTS]; /* map() staging cache */
+	void *flush_buf;     /* L2 flush scratch, allocated on demand */
+	size_t flush_bytes;
+	void *plan_cache;    /* RNS plan cache (opaque, C++) */
+	void *scratch;       /* transform scratch (two-pass out-of-place) */
+	size_t scratch_bytes;
+	uint64_t launches;   /* kernels launched so far */
+};
+
+void device_ctx_init(struct device_ctx *dev, int device);
+void device_ctx_finish(struct device_ctx *dev);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

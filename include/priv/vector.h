@@ -1,0 +1,38 @@
+/*
+ * Device vector.  Mirrors the reference's struct vkhel_vector
+ * (include/priv/vector.h:14-20): a back pointer to the context, the length in
+ * elements, one device buffer and one host staging slot (one outstanding map
+ * per vector).  VkBuffer/VmaAllocation are replaced by plain CUDA pointers.
+ */
+#ifndef PRIV_VECTOR_H
+#define PRIV_VECTOR_H
+
+#include <stdint.h>
+#include <stdlib.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct vkhel_ctx;
+
+struct backing_memory {
+	void *ptr;    /* device pointer (device) or pinned host pointer (host) */
+	size_t bytes; /* capacity */
+};
+
+struct vkhel_vector {
+	struct vkhel_ctx *ctx;
+
+	size_t length;
+	struct backing_memory device;
+	struct backing_memory host; /* non-NULL ptr while mapped */
+};
+
+void vkhel_vector_dbgprint(const struct vkhel_vector *);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

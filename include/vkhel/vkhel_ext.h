@@ -1,0 +1,98 @@
+/*
+ * vkhel B200 extensions -- additive symbols (they match the vkhel_* export
+ * glob of vkhel.syms, so the shared library exports them with no change to
+ * the version script).  The reference API has no batch dimension, no device
+ * argument and no asynchronous transfer; these calls add them
+ * without touching the meaning of the 18 reference entry points.
+ *
+ * Layouts: a batched vector holds `batch` polynomials of ntt->n coefficients
+ * back to back ([batch][n]); an RNS vector holds [batch][limbs][n] with limb l
+ * reduced modulo ntt[l]->q.
+ */
+#ifndef VKHEL_EXT_H
+#define VKHEL_EXT_H
+
+#include <vkhel.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device layer (replaces the reference's src/vulkan.c:153-225) -------- */
+int vkhel_device_count(void);
+/* like vkhel_ctx_create() (reference src/vkhel.c:4-8) but on CUDA device
+ * `device`; vkhel_ctx_create() uses $VKHEL_DEVICE or device 0 (the reference
+ * always takes physical device 0, src/vulkan.c:159-166). */
+struct vkhel_ctx *vkhel_ctx_create_device(int device);
+int vkhel_ctx_device(const struct vkhel_ctx *);
+/* block until everything enqueued on the context has completed (the reference
+ * does this after every op, src/vector.c:327) */
+void vkhel_ctx_sync(struct vkhel_ctx *);
+/* the context's cudaStream_t, for callers that interleave their own work */
+void *vkhel_ctx_stream(struct vkhel_ctx *);
+
+/* ---- pinned host memory + asynchronous transfers --------------------------
+ * (reference: map/unmap staging, src/vector.c:262-296) */
+void *vkhel_host_alloc(size_t bytes);
+void vkhel_host_free(void *);
+uint64_t vkhel_vector_length(const struct vkhel_vector *);
+void *vkhel_vector_device_ptr(struct vkhel_vector *);
+/* enqueue copies of `count` elements starting at element `offset`; the host
+ * buffer must stay valid until vkhel_ctx_sync / map / destroy */
+void vkhel_vector_upload(struct vkhel_vector *, const uint64_t *src,
+		uint64_t offset, uint64_t count);
+void vkhel_vector_download(const struct vkhel_vector *, uint64_t *dst,
+		uint64_t offset, uint64_t count);
+
+/* ---- batched / RNS transforms --------------------------------------------
+ * Same arithmetic per polynomial as vkhel_vector_forward_transform /
+ * vkhel_vector_inverse_transform (reference src/vector.c:513-657); exactly
+ * batch*limbs*n elements are read and written.  result may alias operand. */
+void vkhel_vector_forward_transform_batch(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt, uint64_t batch);
+void vkhel_vector_inverse_transform_batch(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt, uint64_t batch);
+void vkhel_vector_forward_transform_rns(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch);
+void vkhel_vector_inverse_transform_rns(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch);
+
+/* element-wise product / fma with one modulus per limb, [batch][limbs][n]
+ * (per element: reference src/kernels/shaders/elemmul.comp:62-73 and the
+ * canonical elemfma contract) */
+void vkhel_vector_elemmul_rns(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result, const uint64_t *mods,
+		uint64_t limbs, uint64_t n, uint64_t batch);
+
+/* negacyclic polynomial product c = INTT(NTT(a) (*) NTT(b)) per limb, the
+ * reference call sequence forward,forward,elemmul,inverse
+ * (src/vector.c:388-427,513-657) in one call.  a and b are left untouched. */
+void vkhel_vector_polymul_rns(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch);
+
+/* ---- device timing (CUDA events on the context's stream) ----------------- */
+struct vkhel_timer;
+struct vkhel_timer *vkhel_timer_create(struct vkhel_ctx *);
+void vkhel_timer_start(struct vkhel_timer *);
+void vkhel_timer_stop(struct vkhel_timer *);
+/* waits for the stop event; milliseconds between start and stop */
+double vkhel_timer_elapsed_ms(struct vkhel_timer *);
+void vkhel_timer_destroy(struct vkhel_timer *);
+
+/* number of kernels this context has launched so far */
+uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *);
+/* write a buffer larger than L2 so the next kernel starts cold */
+void vkhel_ctx_flush_l2(struct vkhel_ctx *);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

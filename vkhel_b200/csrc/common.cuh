@@ -1,0 +1,88 @@
+/*
+ * Shared declarations of the CUDA side (device layer, vectors, kernels).
+ */
+#ifndef VKHEL_COMMON_CUH
+#define VKHEL_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "priv/vkhel.h"
+#include "priv/ntt_tables.h"
+#include "priv/numbers.h"
+#include "modarith.cuh"
+
+/* Error convention of the reference (assert -> abort): print where
+ * and what, then abort.  Unlike assert() this is never compiled out. */
+#define VK_DIE(...) do { \
+		fprintf(stderr, "vkhel: %s:%d: ", __FILE__, __LINE__); \
+		fprintf(stderr, __VA_ARGS__); \
+		fputc('\n', stderr); \
+		abort(); \
+	} while (0)
+
+#define VK_REQUIRE(cond, ...) do { if (!(cond)) VK_DIE(__VA_ARGS__); } while (0)
+
+#define CUDA_CHECK(call) do { \
+		cudaError_t err__ = (call); \
+		if (err__ != cudaSuccess) \
+			VK_DIE("%s failed: %s", #call, cudaGetErrorString(err__)); \
+	} while (0)
+
+static inline cudaStream_t ctx_stream(const struct vkhel_ctx *ctx) {
+	return (cudaStream_t) ctx->dev.stream;
+}
+
+/* ---- device view of one table (one RNS limb) -------------------------------
+ * tw[k]     = (root[k],     floor(root[k]*2^64/q))      k in [0,n)
+ * tw[n + k] = (inv_root[k], floor(inv_root[k]*2^64/q))
+ * in the reference's bit-reversed order (stage m uses the slice [m, 2m)). */
+struct limb_desc {
+	const ulonglong2 *tw;
+	u64 q;
+	u64 inv_n, inv_n_shoup;       /* n^-1 and its Shoup companion */
+	u64 inv_w1n, inv_w1n_shoup;   /* inv_root[1] * n^-1: last inverse stage */
+	u64 pad_[2];
+};
+
+/* device.cu */
+extern "C" void *device_alloc(struct vkhel_ctx *ctx, size_t bytes);
+extern "C" void device_free(struct vkhel_ctx *ctx, void *ptr);
+extern "C" void *device_scratch(struct vkhel_ctx *ctx, size_t bytes);
+extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes);
+extern "C" void pinned_release(struct vkhel_ctx *ctx, void *ptr);
+/* device pointer to the limb_desc of `ntt` on ctx's device (uploads the
+ * mirror on first use) */
+const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *ntt);
+/* device array of limb_desc for an RNS basis (cached per context) */
+const limb_desc *rns_plan_device_descs(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs);
+
+/* kernels_elem.cu */
+struct modulus make_modulus(uint64_t q);
+void launch_elemmul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, uint64_t len, uint64_t q);
+void launch_elemmul_rns(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, const uint64_t *mods, uint64_t limbs, uint64_t n,
+		uint64_t batch);
+void launch_elemfma(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, uint64_t len, uint64_t mult, uint64_t q);
+void launch_elemmulconst(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t b, uint64_t q);
+void launch_elemgtadd(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t bound, uint64_t diff);
+void launch_elemgtsub(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t bound, uint64_t diff, uint64_t q);
+void launch_elemmodbytwo(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t signed_bound);
+
+/* kernels_ntt.cu: transform `polys` polynomials of n = 2^log2n coefficients,
+ * polynomial p using descs[p % limbs].  dst may equal src. */
+void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
+		const limb_desc *descs, uint64_t limbs, uint64_t polys,
+		unsigned log2n, uint64_t q_max);
+
+#endif

@@ -1,0 +1,435 @@
+/*
+ * CUDA device layer.
+ *
+ * Replaces the reference's Vulkan layer (src/vulkan.c:153-225: instance,
+ * physical device 0, one compute queue, VMA allocator, command pool, eight
+ * pipelines) and its context wrapper (src/vkhel.c:4-13) with:
+ *   - one CUDA device + one non-blocking stream per context (the "queue");
+ *   - a stream-ordered cudaMemPool for vector storage (the VMA role), with an
+ *     unlimited release threshold so create/destroy cycles recycle blocks;
+ *   - a small cache of pinned staging buffers for map()/unmap();
+ *   - lazily uploaded device mirrors of the NTT tables, and a cache of RNS
+ *     descriptor arrays.
+ * Work is enqueued asynchronously; the reference waits on a fence after every
+ * op (src/vector.c:327), here only map/dbgprint/destroy/sync wait.
+ */
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "vkhel_ext.h"
+
+/* cudaSetDevice on the already-current device is a thread-local lookup;
+ * calling it on every entry keeps contexts on different devices (one host
+ * thread each, or interleaved on one thread) independent of each other and of
+ * whatever else in the process moves the current device. */
+static void enter_device(int device) {
+	CUDA_CHECK(cudaSetDevice(device));
+}
+
+static void ctx_enter(const struct vkhel_ctx *ctx) {
+	enter_device(ctx->dev.device);
+}
+
+/* ---- RNS plan cache ------------------------------------------------------- */
+struct rns_plan {
+	std::vector<uint64_t> serials;
+	limb_desc *descs; /* device */
+};
+
+struct plan_cache {
+	std::vector<rns_plan> plans;
+};
+
+/* ---- context -------------------------------------------------------------- */
+extern "C" int vkhel_device_count(void) {
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess) {
+		(void) cudaGetLastError();
+		return 0;
+	}
+	return count;
+}
+
+extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess || count == 0) {
+		VK_DIE("no usable CUDA device (%s); vkhel has no CPU fallback",
+				err != cudaSuccess ? cudaGetErrorString(err)
+				: "device count is 0");
+	}
+	VK_REQUIRE(device >= 0 && device < count,
+			"device %d out of range (have %d)", device, count);
+	VK_REQUIRE(device < VKHEL_MAX_DEVICES,
+			"device ordinal %d not supported", device);
+
+	memset(dev, 0, sizeof(*dev));
+	dev->device = device;
+	enter_device(device);
+
+	cudaDeviceProp prop;
+	CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+	VK_REQUIRE(prop.major >= 10,
+			"device %d (%s) is sm_%d%d; this build carries sm_100a code only",
+			device, prop.name, prop.major, prop.minor);
+	dev->sm_count = prop.multiProcessorCount;
+	dev->smem_optin = prop.sharedMemPerBlockOptin;
+	dev->l2_bytes = (size_t) prop.l2CacheSize;
+
+	/* the reference prints its choice too (src/vulkan.c:171-172) */
+	printf("using physical device %d: %s\n", device, prop.name);
+	fflush(stdout);
+
+	cudaStream_t stream;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	dev->stream = stream;
+
+	cudaMemPoolProps props;
+	memset(&props, 0, sizeof(props));
+	props.allocType = cudaMemAllocationTypePinned;
+	props.handleTypes = cudaMemHandleTypeNone;
+	props.location.type = cudaMemLocationTypeDevice;
+	props.location.id = device;
+	cudaMemPool_t pool;
+	CUDA_CHECK(cudaMemPoolCreate(&pool, &props));
+	uint64_t threshold = UINT64_MAX;
+	CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
+				&threshold));
+	dev->mem_pool = pool;
+
+	dev->plan_cache = new plan_cache();
+}
+
+extern "C" void device_ctx_finish(struct device_ctx *dev) {
+	enter_device(dev->device);
+	cudaStream_t stream = (cudaStream_t) dev->stream;
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+
+	plan_cache *cache = (plan_cache *) dev->plan_cache;
+	for (rns_plan &plan : cache->plans) {
+		CUDA_CHECK(cudaFree(plan.descs));
+	}
+	delete cache;
+
+	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
+		if (dev->pinned[i].ptr) {
+			CUDA_CHECK(cudaFreeHost(dev->pinned[i].ptr));
+		}
+	}
+	if (dev->flush_buf) {
+		CUDA_CHECK(cudaFree(dev->flush_buf));
+	}
+	if (dev->scratch) {
+		CUDA_CHECK(cudaFree(dev->scratch));
+	}
+	CUDA_CHECK(cudaMemPoolDestroy((cudaMemPool_t) dev->mem_pool));
+	CUDA_CHECK(cudaStreamDestroy(stream));
+	memset(dev, 0, sizeof(*dev));
+}
+
+extern "C" struct vkhel_ctx *vkhel_ctx_create_device(int device) {
+	struct vkhel_ctx *ctx = (struct vkhel_ctx *) calloc(1, sizeof(*ctx));
+	VK_REQUIRE(ctx, "out of host memory");
+	device_ctx_init(&ctx->dev, device);
+	return ctx;
+}
+
+extern "C" struct vkhel_ctx *vkhel_ctx_create(void) {
+	int device = 0;
+	const char *env = getenv("VKHEL_DEVICE");
+	if (env && *env) {
+		device = atoi(env);
+	}
+	return vkhel_ctx_create_device(device);
+}
+
+extern "C" void vkhel_ctx_destroy(struct vkhel_ctx *ctx) {
+	if (!ctx) {
+		return;
+	}
+	device_ctx_finish(&ctx->dev);
+	free(ctx);
+}
+
+extern "C" int vkhel_ctx_device(const struct vkhel_ctx *ctx) {
+	return ctx->dev.device;
+}
+
+extern "C" void vkhel_ctx_sync(struct vkhel_ctx *ctx) {
+	ctx_enter(ctx);
+	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
+}
+
+extern "C" void *vkhel_ctx_stream(struct vkhel_ctx *ctx) {
+	return ctx->dev.stream;
+}
+
+extern "C" uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *ctx) {
+	return ctx->dev.launches;
+}
+
+extern "C" void vkhel_ctx_flush_l2(struct vkhel_ctx *ctx) {
+	ctx_enter(ctx);
+	struct device_ctx *dev = &ctx->dev;
+	if (!dev->flush_buf) {
+		/* twice the L2 so that every line is displaced */
+		dev->flush_bytes = dev->l2_bytes ? 2 * dev->l2_bytes : (256u << 20);
+		CUDA_CHECK(cudaMalloc(&dev->flush_buf, dev->flush_bytes));
+	}
+	CUDA_CHECK(cudaMemsetAsync(dev->flush_buf, 0x5a, dev->flush_bytes,
+				ctx_stream(ctx)));
+}
+
+/* ---- memory --------------------------------------------------------------- */
+extern "C" void *device_alloc(struct vkhel_ctx *ctx, size_t bytes) {
+	ctx_enter(ctx);
+	void *ptr = NULL;
+	if (bytes == 0) {
+		bytes = 8;
+	}
+	CUDA_CHECK(cudaMallocFromPoolAsync(&ptr, bytes,
+				(cudaMemPool_t) ctx->dev.mem_pool, ctx_stream(ctx)));
+	return ptr;
+}
+
+extern "C" void device_free(struct vkhel_ctx *ctx, void *ptr) {
+	ctx_enter(ctx);
+	if (ptr) {
+		CUDA_CHECK(cudaFreeAsync(ptr, ctx_stream(ctx)));
+	}
+}
+
+/* grow-only scratch buffer owned by the context (stream-ordered use only) */
+extern "C" void *device_scratch(struct vkhel_ctx *ctx, size_t bytes) {
+	ctx_enter(ctx);
+	struct device_ctx *dev = &ctx->dev;
+	if (dev->scratch_bytes < bytes) {
+		if (dev->scratch) {
+			CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
+			CUDA_CHECK(cudaFree(dev->scratch));
+		}
+		CUDA_CHECK(cudaMalloc(&dev->scratch, bytes));
+		dev->scratch_bytes = bytes;
+	}
+	return dev->scratch;
+}
+
+extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes) {
+	ctx_enter(ctx);
+	struct device_ctx *dev = &ctx->dev;
+	if (bytes == 0) {
+		bytes = 8;
+	}
+	int free_slot = -1;
+	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
+		struct pinned_slot *slot = &dev->pinned[i];
+		if (slot->in_use) {
+			continue;
+		}
+		if (slot->ptr && slot->bytes >= bytes) {
+			slot->in_use = 1;
+			return slot->ptr;
+		}
+		if (free_slot < 0 || !slot->ptr) {
+			free_slot = i;
+		}
+	}
+	void *ptr = NULL;
+	if (free_slot < 0) {
+		/* more simultaneous maps than cache slots: uncached allocation */
+		CUDA_CHECK(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
+		return ptr;
+	}
+	struct pinned_slot *slot = &dev->pinned[free_slot];
+	if (slot->ptr) {
+		CUDA_CHECK(cudaFreeHost(slot->ptr));
+	}
+	CUDA_CHECK(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
+	slot->ptr = ptr;
+	slot->bytes = bytes;
+	slot->in_use = 1;
+	return ptr;
+}
+
+extern "C" void pinned_release(struct vkhel_ctx *ctx, void *ptr) {
+	ctx_enter(ctx);
+	struct device_ctx *dev = &ctx->dev;
+	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
+		if (dev->pinned[i].ptr == ptr) {
+			dev->pinned[i].in_use = 0;
+			return;
+		}
+	}
+	CUDA_CHECK(cudaFreeHost(ptr));
+}
+
+extern "C" void *vkhel_host_alloc(size_t bytes) {
+	void *ptr = NULL;
+	CUDA_CHECK(cudaHostAlloc(&ptr, bytes ? bytes : 8, cudaHostAllocPortable));
+	return ptr;
+}
+
+extern "C" void vkhel_host_free(void *ptr) {
+	if (ptr) {
+		CUDA_CHECK(cudaFreeHost(ptr));
+	}
+}
+
+/* ---- NTT table device mirrors -------------------------------------------------
+ * Layout of one mirror: [limb_desc (64 B)][2n pairs of (w, w')].  The tables
+ * object has no context (reference src/ntt_tables.c:65-87), so the mirror is
+ * a plain cudaMalloc keyed by device ordinal and freed in tables_destroy. */
+static void fill_desc(const struct vkhel_ntt_tables *ntt, limb_desc *desc,
+		const ulonglong2 *dev_pairs) {
+	const uint64_t n = ntt->n;
+	memset(desc, 0, sizeof(*desc));
+	desc->tw = dev_pairs;
+	desc->q = ntt->q;
+	desc->inv_n = ntt->inv_n;
+	desc->inv_n_shoup = ntt->inv_n_shoup;
+	if (n >= 2) {
+		desc->inv_w1n = nt_multiply_mod(ntt->inv_roots_of_unity[1],
+				ntt->inv_n, ntt->q, 0);
+		desc->inv_w1n_shoup = nt_compute_barrett_factor(desc->inv_w1n,
+				ntt->q, 64);
+	}
+}
+
+static void *ensure_mirror(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *ntt) {
+	const int device = ctx->dev.device;
+	if (ntt->dev_pairs[device]) {
+		return ntt->dev_pairs[device];
+	}
+	ctx_enter(ctx);
+	VK_REQUIRE(ntt->q < (1ull << 63),
+			"NTT modulus must be below 2^63 (as in the reference, whose "
+			"nt_inverse_mod works in int64_t)");
+	const size_t pair_bytes = 2 * ntt->n * sizeof(ulonglong2);
+	const size_t bytes = sizeof(limb_desc) + pair_bytes;
+	char *dev_buf = NULL;
+	CUDA_CHECK(cudaMalloc(&dev_buf, bytes));
+	char *host_buf = (char *) malloc(bytes);
+	VK_REQUIRE(host_buf, "out of host memory");
+	fill_desc(ntt, (limb_desc *) host_buf,
+			(const ulonglong2 *) (dev_buf + sizeof(limb_desc)));
+	ulonglong2 *pairs = (ulonglong2 *) (host_buf + sizeof(limb_desc));
+	for (uint64_t k = 0; k < ntt->n; k++) {
+		pairs[k] = make_ulonglong2(ntt->roots_of_unity[k],
+				ntt->roots_barrett_factors[k]);
+		pairs[ntt->n + k] = make_ulonglong2(ntt->inv_roots_of_unity[k],
+				ntt->inv_roots_barrett_factors[k]);
+	}
+	/* synchronous copy: complete before any kernel that reads it is
+	 * enqueued, and the host buffer can be freed right away */
+	CUDA_CHECK(cudaMemcpy(dev_buf, host_buf, bytes, cudaMemcpyHostToDevice));
+	free(host_buf);
+	ntt->dev_pairs[device] = dev_buf;
+	return dev_buf;
+}
+
+const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *ntt) {
+	return (const limb_desc *) ensure_mirror(ctx, ntt);
+}
+
+extern "C" void ntt_tables_release_device(struct vkhel_ntt_tables *ntt) {
+	for (int device = 0; device < VKHEL_MAX_DEVICES; device++) {
+		if (!ntt->dev_pairs[device]) {
+			continue;
+		}
+		enter_device(device);
+		/* cudaFree waits for work that may still read the mirror */
+		CUDA_CHECK(cudaFree(ntt->dev_pairs[device]));
+		ntt->dev_pairs[device] = NULL;
+	}
+}
+
+const limb_desc *rns_plan_device_descs(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs) {
+	plan_cache *cache = (plan_cache *) ctx->dev.plan_cache;
+	for (rns_plan &plan : cache->plans) {
+		if (plan.serials.size() != limbs) {
+			continue;
+		}
+		bool same = true;
+		for (uint64_t l = 0; l < limbs && same; l++) {
+			same = plan.serials[l] == ntt[l]->serial
+				&& ntt[l]->dev_pairs[ctx->dev.device] != NULL;
+		}
+		if (same) {
+			return plan.descs;
+		}
+	}
+	ctx_enter(ctx);
+	std::vector<limb_desc> host(limbs);
+	rns_plan plan;
+	for (uint64_t l = 0; l < limbs; l++) {
+		VK_REQUIRE(ntt[l]->n == ntt[0]->n,
+				"all limbs of an RNS basis must share n");
+		const char *mirror = (const char *) ensure_mirror(ctx, ntt[l]);
+		/* the header of the mirror is the limb's descriptor: rebuild it on
+		 * the host instead of reading it back */
+		fill_desc(ntt[l], &host[l],
+				(const ulonglong2 *) (mirror + sizeof(limb_desc)));
+		plan.serials.push_back(ntt[l]->serial);
+	}
+	CUDA_CHECK(cudaMalloc(&plan.descs, limbs * sizeof(limb_desc)));
+	CUDA_CHECK(cudaMemcpy(plan.descs, host.data(), limbs * sizeof(limb_desc),
+				cudaMemcpyHostToDevice));
+	/* bound the cache: drop the oldest plan beyond 64 entries */
+	if (cache->plans.size() >= 64) {
+		CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
+		CUDA_CHECK(cudaFree(cache->plans.front().descs));
+		cache->plans.erase(cache->plans.begin());
+	}
+	cache->plans.push_back(plan);
+	return plan.descs;
+}
+
+/* ---- timers --------------------------------------------------------------- */
+struct vkhel_timer {
+	struct vkhel_ctx *ctx;
+	cudaEvent_t start, stop;
+};
+
+extern "C" struct vkhel_timer *vkhel_timer_create(struct vkhel_ctx *ctx) {
+	ctx_enter(ctx);
+	struct vkhel_timer *timer =
+		(struct vkhel_timer *) calloc(1, sizeof(*timer));
+	VK_REQUIRE(timer, "out of host memory");
+	timer->ctx = ctx;
+	CUDA_CHECK(cudaEventCreate(&timer->start));
+	CUDA_CHECK(cudaEventCreate(&timer->stop));
+	return timer;
+}
+
+extern "C" void vkhel_timer_start(struct vkhel_timer *timer) {
+	ctx_enter(timer->ctx);
+	CUDA_CHECK(cudaEventRecord(timer->start, ctx_stream(timer->ctx)));
+}
+
+extern "C" void vkhel_timer_stop(struct vkhel_timer *timer) {
+	ctx_enter(timer->ctx);
+	CUDA_CHECK(cudaEventRecord(timer->stop, ctx_stream(timer->ctx)));
+}
+
+extern "C" double vkhel_timer_elapsed_ms(struct vkhel_timer *timer) {
+	ctx_enter(timer->ctx);
+	CUDA_CHECK(cudaEventSynchronize(timer->stop));
+	float ms = 0.0f;
+	CUDA_CHECK(cudaEventElapsedTime(&ms, timer->start, timer->stop));
+	return (double) ms;
+}
+
+extern "C" void vkhel_timer_destroy(struct vkhel_timer *timer) {
+	if (!timer) {
+		return;
+	}
+	ctx_enter(timer->ctx);
+	CUDA_CHECK(cudaEventDestroy(timer->start));
+	CUDA_CHECK(cudaEventDestroy(timer->stop));
+	free(timer);
+}

@@ -1,0 +1,284 @@
+/*
+ * Element-wise kernels: the sm_100a replacements of the reference's
+ * elemmul / elemfma / elemmulconst / elemgtadd / elemgtsub / elemmodbytwo
+ * compute shaders (src/kernels/shaders/X.comp) and of their record functions
+ * (src/kernels/X.c), which computed the Barrett constants per call.
+ *
+ * All of them are HBM-bound streaming kernels (24 or 16 bytes per element,
+ * a few dozen integer instructions): 128-bit coalesced loads and stores, two
+ * vectors in flight per thread, grid sized to whole waves of the SM count.
+ * Each output is the canonical residue, so results are bit-identical to the
+ * shaders wherever those are defined.
+ */
+#include "common.cuh"
+
+typedef unsigned __int128 u128;
+
+struct modulus make_modulus(uint64_t q) {
+	VK_REQUIRE(q >= 2, "modulus must be at least 2");
+	struct modulus m;
+	m.q = q;
+	m.mu = (u64) ((((u128) 1) << 64) / q);
+	m.s = (unsigned) __builtin_clzll(q);
+	m.d = q << m.s;
+	m.v = (u64) ((~(u128) 0) / m.d - (((u128) 1) << 64));
+	return m;
+}
+
+/* ---- per-element operations ------------------------------------------------------ */
+struct op_mul { /* reference elemmul.comp:62-73 */
+	modulus m;
+	__device__ __forceinline__ u64 operator()(u64 a, u64 b) const {
+		return mulmod(reduce64(a, m), reduce64(b, m), m);
+	}
+};
+
+struct op_fma { /* contract of elemfma (shader defect Q2) */
+	modulus m;
+	u64 mult; /* already reduced */
+	__device__ __forceinline__ u64 operator()(u64 a, u64 b) const {
+		const u64 ar = reduce64(a, m);
+		const u64 br = reduce64(b, m);
+		/* ar*mult + br <= (q-1)^2 + (q-1) < q^2: high word stays below q */
+		const u64 lo = ar * mult;
+		const u64 sum = lo + br;
+		const u64 hi = __umul64hi(ar, mult) + (sum < lo);
+		return reduce128(hi, sum, m);
+	}
+};
+
+struct op_mulconst { /* reference elemmulconst.comp:35-49 */
+	u64 q, b, bp;
+	__device__ __forceinline__ u64 operator()(u64 a, u64) const {
+		return shoup_canon(a, b, bp, q);
+	}
+};
+
+struct op_mulconst_wide { /* same for q >= 2^63 where Shoup's range breaks */
+	modulus m;
+	u64 b;
+	__device__ __forceinline__ u64 operator()(u64 a, u64) const {
+		return mulmod(reduce64(a, m), b, m);
+	}
+};
+
+struct op_gtadd { /* reference elemgtadd.comp:20-30 */
+	u64 bound, diff;
+	__device__ __forceinline__ u64 operator()(u64 a, u64) const {
+		return a > bound ? a + diff : a;
+	}
+};
+
+struct op_gtsub { /* reference elemgtsub.comp:49-67 */
+	modulus m;
+	u64 bound, diff; /* diff already reduced */
+	__device__ __forceinline__ u64 operator()(u64 a, u64) const {
+		const u64 r = reduce64(a, m);
+		if (a > bound) { /* the compare uses the unreduced input */
+			return r >= diff ? r - diff : r + (m.q - diff);
+		}
+		return r;
+	}
+};
+
+struct op_modbytwo { /* reference elemmodbytwo.comp:19-27 */
+	u64 signed_bound;
+	__device__ __forceinline__ u64 operator()(u64 a, u64) const {
+		const u64 u = a & 1;
+		return a > signed_bound ? 1 - u : u;
+	}
+};
+
+/* ---- streaming skeleton -------------------------------------------------------------
+ * result may alias an operand (in-place ops), hence no __restrict__.
+ * Vector body: each thread handles UNROLL 16-byte vectors per iteration, all
+ * loads issued before the first use.  `len` elements; pointers 16 B aligned
+ * (the scalar kernel below covers odd tails and unaligned sub-ranges). */
+#define ELEM_THREADS 256
+#define ELEM_UNROLL 4
+
+template <bool TWO_INPUTS, class Op>
+__global__ void __launch_bounds__(ELEM_THREADS)
+elem_vec_kernel(const ulonglong2 *a,
+		const ulonglong2 *b, ulonglong2 *out,
+		u64 nvec, const Op op) {
+	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
+	u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x;
+	for (; i + (ELEM_UNROLL - 1) * stride < nvec; i += ELEM_UNROLL * stride) {
+		ulonglong2 va[ELEM_UNROLL], vb[ELEM_UNROLL];
+#pragma unroll
+		for (int u = 0; u < ELEM_UNROLL; u++) {
+			va[u] = a[i + u * stride];
+			if (TWO_INPUTS) {
+				vb[u] = b[i + u * stride];
+			} else {
+				vb[u] = make_ulonglong2(0, 0);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < ELEM_UNROLL; u++) {
+			out[i + u * stride] = make_ulonglong2(op(va[u].x, vb[u].x),
+					op(va[u].y, vb[u].y));
+		}
+	}
+	for (; i < nvec; i += stride) {
+		const ulonglong2 va = a[i];
+		const ulonglong2 vb = TWO_INPUTS ? b[i] : make_ulonglong2(0, 0);
+		out[i] = make_ulonglong2(op(va.x, vb.x), op(va.y, vb.y));
+	}
+}
+
+template <bool TWO_INPUTS, class Op>
+__global__ void __launch_bounds__(ELEM_THREADS)
+elem_scalar_kernel(const u64 *a, const u64 *b, u64 *out, u64 len,
+		const Op op) {
+	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
+	for (u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x; i < len;
+			i += stride) {
+		out[i] = op(a[i], TWO_INPUTS ? b[i] : 0);
+	}
+}
+
+static unsigned grid_for(const struct vkhel_ctx *ctx, u64 work_items,
+		unsigned per_block) {
+	const u64 blocks = (work_items + per_block - 1) / per_block;
+	/* at most 8 resident 256-thread CTAs per SM: one full wave */
+	const u64 wave = (u64) ctx->dev.sm_count * 8;
+	return (unsigned) (blocks < wave ? (blocks ? blocks : 1) : wave);
+}
+
+template <bool TWO_INPUTS, class Op>
+static void launch_elem(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, uint64_t len, const Op &op) {
+	if (len == 0) {
+		return;
+	}
+	cudaStream_t stream = ctx_stream(ctx);
+	const uintptr_t align = (uintptr_t) a | (uintptr_t) out
+		| (TWO_INPUTS ? (uintptr_t) b : 0);
+	uint64_t done = 0;
+	if ((align & 15) == 0 && len >= 2) {
+		const u64 nvec = len / 2;
+		elem_vec_kernel<TWO_INPUTS, Op>
+			<<<grid_for(ctx, nvec, ELEM_THREADS * ELEM_UNROLL),
+				ELEM_THREADS, 0, stream>>>(
+				(const ulonglong2 *) a, (const ulonglong2 *) b,
+				(ulonglong2 *) out, nvec, op);
+		CUDA_CHECK(cudaGetLastError());
+		ctx->dev.launches++;
+		done = nvec * 2;
+	}
+	if (done < len) {
+		const u64 rest = len - done;
+		elem_scalar_kernel<TWO_INPUTS, Op>
+			<<<grid_for(ctx, rest, ELEM_THREADS), ELEM_THREADS, 0, stream>>>(
+				a + done, TWO_INPUTS ? b + done : NULL, out + done, rest, op);
+		CUDA_CHECK(cudaGetLastError());
+		ctx->dev.launches++;
+	}
+}
+
+void launch_elemmul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, uint64_t len, uint64_t q) {
+	op_mul op = { make_modulus(q) };
+	launch_elem<true>(ctx, a, b, out, len, op);
+}
+
+void launch_elemfma(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, uint64_t len, uint64_t mult, uint64_t q) {
+	op_fma op = { make_modulus(q), mult % q };
+	launch_elem<true>(ctx, a, b, out, len, op);
+}
+
+void launch_elemmulconst(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t b, uint64_t q) {
+	if (q >> 63) {
+		op_mulconst_wide op = { make_modulus(q), b % q };
+		launch_elem<false>(ctx, in, NULL, out, len, op);
+		return;
+	}
+	b %= q;
+	op_mulconst op = { q, b, nt_compute_barrett_factor(b, q, 64) };
+	launch_elem<false>(ctx, in, NULL, out, len, op);
+}
+
+void launch_elemgtadd(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t bound, uint64_t diff) {
+	op_gtadd op = { bound, diff };
+	launch_elem<false>(ctx, in, NULL, out, len, op);
+}
+
+void launch_elemgtsub(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t bound, uint64_t diff, uint64_t q) {
+	op_gtsub op = { make_modulus(q), bound, diff % q };
+	launch_elem<false>(ctx, in, NULL, out, len, op);
+}
+
+void launch_elemmodbytwo(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
+		uint64_t len, uint64_t signed_bound) {
+	op_modbytwo op = { signed_bound };
+	launch_elem<false>(ctx, in, NULL, out, len, op);
+}
+
+/* ---- RNS element-wise product: [batch][limbs][n], one modulus per limb ------------- */
+#define RNS_MAX_LIMBS 64
+
+struct rns_moduli {
+	modulus m[RNS_MAX_LIMBS];
+};
+
+__global__ void __launch_bounds__(ELEM_THREADS)
+elemmul_rns_kernel(const ulonglong2 *a,
+		const ulonglong2 *b, ulonglong2 *out,
+		u64 nvec, unsigned log2_vec_per_poly, unsigned limbs,
+		const __grid_constant__ rns_moduli mods) {
+	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
+	for (u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x; i < nvec;
+			i += 2 * stride) {
+		const u64 j = i + stride;
+		const bool second = j < nvec;
+		const ulonglong2 a0 = a[i], b0 = b[i];
+		ulonglong2 a1 = make_ulonglong2(0, 0), b1 = a1;
+		if (second) {
+			a1 = a[j];
+			b1 = b[j];
+		}
+		const modulus &m0 = mods.m[(i >> log2_vec_per_poly) % limbs];
+		out[i] = make_ulonglong2(
+				mulmod(reduce64(a0.x, m0), reduce64(b0.x, m0), m0),
+				mulmod(reduce64(a0.y, m0), reduce64(b0.y, m0), m0));
+		if (second) {
+			const modulus &m1 = mods.m[(j >> log2_vec_per_poly) % limbs];
+			out[j] = make_ulonglong2(
+					mulmod(reduce64(a1.x, m1), reduce64(b1.x, m1), m1),
+					mulmod(reduce64(a1.y, m1), reduce64(b1.y, m1), m1));
+		}
+	}
+}
+
+void launch_elemmul_rns(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *out, const uint64_t *mods, uint64_t limbs, uint64_t n,
+		uint64_t batch) {
+	VK_REQUIRE(limbs >= 1 && limbs <= RNS_MAX_LIMBS,
+			"elemmul_rns: 1..%d limbs", RNS_MAX_LIMBS);
+	VK_REQUIRE(n >= 2 && (n & (n - 1)) == 0,
+			"elemmul_rns: n must be a power of two >= 2");
+	if (batch == 0) {
+		return;
+	}
+	rns_moduli params;
+	for (uint64_t l = 0; l < limbs; l++) {
+		params.m[l] = make_modulus(mods[l]);
+	}
+	for (uint64_t l = limbs; l < RNS_MAX_LIMBS; l++) {
+		params.m[l] = params.m[0];
+	}
+	const u64 nvec = limbs * n * batch / 2;
+	const unsigned log2_vec_per_poly = (unsigned) nt_ceil_log2(n) - 2;
+	elemmul_rns_kernel<<<grid_for(ctx, nvec, ELEM_THREADS * 2), ELEM_THREADS,
+		0, ctx_stream(ctx)>>>((const ulonglong2 *) a, (const ulonglong2 *) b,
+				(ulonglong2 *) out, nvec, log2_vec_per_poly, (unsigned) limbs,
+				params);
+	CUDA_CHECK(cudaGetLastError());
+	ctx->dev.launches++;
+}

@@ -1,0 +1,128 @@
+/*
+ * Device-side 64-bit modular arithmetic for sm_100a.
+ *
+ * Everything here produces the same residues as the reference's GLSL
+ * arithmetic (src/kernels/shaders/X.comp), which emulates 64x64->128 products
+ * with four 32x32 multiplies (e.g. nttfwdbutterfly.comp:21-29); on sm_100a the
+ * high half comes from mul.hi.u64 (IMAD.WIDE.U32 chains).  Because every
+ * reference kernel stores the canonical residue in [0,q), any exact algorithm
+ * followed by a canonical reduction is bit-identical to it.
+ */
+#ifndef VKHEL_MODARITH_CUH
+#define VKHEL_MODARITH_CUH
+
+#include <stdint.h>
+
+typedef unsigned long long u64;
+
+/* ---- Shoup multiplication by a fixed factor --------------------------------
+ * w < q, wp = floor(w * 2^64 / q).  For ANY 64-bit y the lazy result is
+ * y*w mod q + {0,q}, i.e. in [0,2q) (reference: nttfwdbutterfly.comp:44-48,
+ * elemmulconst.comp:42-46, which then subtract q once). Needs q < 2^63. */
+__device__ __forceinline__ u64 shoup_lazy(u64 y, u64 w, u64 wp, u64 q) {
+	return y * w - __umul64hi(y, wp) * q;
+}
+
+__device__ __forceinline__ u64 shoup_canon(u64 y, u64 w, u64 wp, u64 q) {
+	const u64 r = shoup_lazy(y, w, wp, q);
+	return r >= q ? r - q : r;
+}
+
+/* x - (x >= m ? m : 0) */
+__device__ __forceinline__ u64 csub(u64 x, u64 m) {
+	return x >= m ? x - m : x;
+}
+
+/* ---- Harvey butterflies, lazy ranges (q < 2^62) ------------------------------
+ * forward (Cooley-Tukey, reference nttfwdbutterfly.comp:41-57):
+ *   in : x, y in [0,4q)      out: x' = x + w*y, y' = x - w*y, both in [0,4q)
+ * inverse (Gentleman-Sande, reference nttrevbutterfly.comp:41-57):
+ *   in : x, y in [0,2q)      out: x' = x + y, y' = (x - y)*w, both in [0,2q)
+ */
+__device__ __forceinline__ void ct_lazy(u64 &x, u64 &y, u64 w, u64 wp,
+		u64 q, u64 twoq) {
+	const u64 xr = csub(x, twoq);
+	const u64 t = shoup_lazy(y, w, wp, q);
+	x = xr + t;
+	y = xr - t + twoq;
+}
+
+__device__ __forceinline__ void gs_lazy(u64 &x, u64 &y, u64 w, u64 wp,
+		u64 q, u64 twoq) {
+	const u64 s = x + y;
+	const u64 d = x - y + twoq;
+	x = csub(s, twoq);
+	y = shoup_lazy(d, w, wp, q);
+}
+
+/* ---- strict butterflies: every value canonical (2^62 <= q < 2^63) ---------- */
+__device__ __forceinline__ void ct_strict(u64 &x, u64 &y, u64 w, u64 wp,
+		u64 q) {
+	const u64 t = shoup_canon(y, w, wp, q);
+	const u64 s = x + t;           /* < 2q < 2^64 */
+	const u64 d = x - t;
+	y = x < t ? d + q : d;
+	x = csub(s, q);
+}
+
+__device__ __forceinline__ void gs_strict(u64 &x, u64 &y, u64 w, u64 wp,
+		u64 q) {
+	const u64 s = x + y;
+	const u64 d = x - y;
+	const u64 dd = x < y ? d + q : d;
+	x = csub(s, q);
+	y = shoup_canon(dd, w, wp, q);
+}
+
+/* ---- general reduction for the element-wise kernels -------------------------
+ * Exact for every modulus 2 <= q < 2^64 and every input, which covers the
+ * reference tests' tiny moduli (2, 3, 5, 10, 17: test/vector.c:167-241,
+ * examples/example.c:47) where the reference's own Barrett shift is
+ * ill-defined.
+ *
+ * struct modulus is built on the host (make_modulus in vector.cu):
+ *   mu   = floor(2^64 / q)                       one-word reciprocal
+ *   s    = clz(q), d = q << s                    normalised divisor
+ *   v    = floor((2^128 - 1) / d) - 2^64         Moller-Granlund reciprocal
+ */
+struct modulus {
+	u64 q;
+	u64 mu;
+	u64 d;
+	u64 v;
+	unsigned s;
+};
+
+/* x mod q, any 64-bit x */
+__device__ __forceinline__ u64 reduce64(u64 x, const modulus &m) {
+	/* floor(x*mu/2^64) is floor(x/q) or one less */
+	const u64 r = x - __umul64hi(x, m.mu) * m.q;
+	return r >= m.q ? r - m.q : r;
+}
+
+/* (hi*2^64 + lo) mod q for hi < q: division of a two-word numerator by a
+ * normalised one-word divisor (Moller & Granlund 2011, Alg. 4) */
+__device__ __forceinline__ u64 reduce128(u64 hi, u64 lo, const modulus &m) {
+	const u64 u1 = m.s ? (hi << m.s) | (lo >> (64 - m.s)) : hi;
+	const u64 u0 = lo << m.s;
+	/* (q1,q0) = v*u1 + (u1,u0) */
+	u64 q0 = m.v * u1;
+	u64 q1 = __umul64hi(m.v, u1);
+	q0 += u0;
+	q1 += u1 + (q0 < u0) + 1;
+	u64 r = u0 - q1 * m.d;
+	if (r > q0) {
+		r += m.d;
+	}
+	if (r >= m.d) {
+		r -= m.d;
+	}
+	return r >> m.s;
+}
+
+/* a*b mod q for a, b < q */
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const modulus &m) {
+	return reduce128(__umul64hi(a, b), a * b, m);
+}
+
+#endif

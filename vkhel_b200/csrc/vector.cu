@@ -1,0 +1,419 @@
+/*
+ * Vectors and the operator entry points.
+ *
+ * Host side of the reference's src/vector.c retargeted to the CUDA device
+ * layer: buffer lifecycle (vector.c:206-260), map/unmap staging
+ * (vector.c:262-296), the element-wise entry points (vector.c:298-511) and the
+ * forward/inverse transforms (vector.c:513-657).  Where the reference records
+ * one dispatch per butterfly group and waits on a fence per stage, each entry
+ * point here enqueues one or two kernels on the context's stream and returns.
+ */
+#include <inttypes.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "vkhel_ext.h"
+
+static void enter(const struct vkhel_ctx *ctx) {
+	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+}
+
+static inline u64 *dev_u64(const struct vkhel_vector *v) {
+	return (u64 *) v->device.ptr;
+}
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+extern "C" struct vkhel_vector *vkhel_vector_create2(struct vkhel_ctx *ctx,
+		uint64_t length, bool zero) {
+	VK_REQUIRE(ctx, "vkhel_vector_create: NULL context");
+	struct vkhel_vector *vec =
+		(struct vkhel_vector *) calloc(1, sizeof(*vec));
+	VK_REQUIRE(vec, "out of host memory");
+	vec->ctx = ctx;
+	vec->length = length;
+	vec->device.bytes = length * sizeof(uint64_t);
+	vec->device.ptr = device_alloc(ctx, vec->device.bytes);
+	if (zero && length) {
+		/* reference: vkCmdFillBuffer(0), src/vector.c:152-204 */
+		CUDA_CHECK(cudaMemsetAsync(vec->device.ptr, 0, vec->device.bytes,
+					ctx_stream(ctx)));
+	}
+	return vec;
+}
+
+extern "C" struct vkhel_vector *vkhel_vector_create(struct vkhel_ctx *ctx,
+		uint64_t length) {
+	return vkhel_vector_create2(ctx, length, true);
+}
+
+extern "C" void vkhel_vector_destroy(struct vkhel_vector *vec) {
+	if (!vec) {
+		return;
+	}
+	struct vkhel_ctx *ctx = vec->ctx;
+	if (vec->host.ptr) {
+		/* destroyed while mapped: drop the staging buffer, nothing is
+		 * written back */
+		pinned_release(ctx, vec->host.ptr);
+	}
+	/* stream-ordered free: work already enqueued on the stream completes
+	 * before the block is reused */
+	device_free(ctx, vec->device.ptr);
+	free(vec);
+}
+
+extern "C" struct vkhel_vector *vkhel_vector_dup(struct vkhel_vector *src) {
+	/* no zero fill: about to be overwritten (reference vector.c:249-260) */
+	struct vkhel_vector *dup = vkhel_vector_create2(src->ctx, src->length,
+			false);
+	if (src->length) {
+		CUDA_CHECK(cudaMemcpyAsync(dup->device.ptr, src->device.ptr,
+					src->device.bytes, cudaMemcpyDeviceToDevice,
+					ctx_stream(src->ctx)));
+	}
+	return dup;
+}
+
+extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
+		const uint64_t *elements) {
+	/* The reference maps (a device->host copy it does not need), memcpys and
+	 * unmaps (vector.c:262-268).  Here: one host->device copy.  The source
+	 * may be pageable and may be reused by the caller as soon as this
+	 * returns, so the copy is completed before returning. */
+	if (!vec->length) {
+		return;
+	}
+	enter(vec->ctx);
+	CUDA_CHECK(cudaMemcpyAsync(vec->device.ptr, elements, vec->device.bytes,
+				cudaMemcpyHostToDevice, ctx_stream(vec->ctx)));
+	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
+}
+
+extern "C" void vkhel_vector_map(struct vkhel_vector *vec, void **mem,
+		size_t size) {
+	/* `size` is in bytes in the reference's tests and in elements in its
+	 * example; staging the whole vector serves both. */
+	(void) size;
+	VK_REQUIRE(!vec->host.ptr, "vector is already mapped");
+	enter(vec->ctx);
+	vec->host.bytes = vec->device.bytes;
+	vec->host.ptr = pinned_acquire(vec->ctx, vec->host.bytes);
+	if (vec->length) {
+		CUDA_CHECK(cudaMemcpyAsync(vec->host.ptr, vec->device.ptr,
+					vec->device.bytes, cudaMemcpyDeviceToHost,
+					ctx_stream(vec->ctx)));
+	}
+	/* everything enqueued before the map is now visible to the host */
+	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
+	*mem = vec->host.ptr;
+}
+
+extern "C" void vkhel_vector_unmap(struct vkhel_vector *vec) {
+	VK_REQUIRE(vec->host.ptr, "vector is not mapped");
+	enter(vec->ctx);
+	/* the whole vector is written back (reference vector.c:291) */
+	if (vec->length) {
+		CUDA_CHECK(cudaMemcpyAsync(vec->device.ptr, vec->host.ptr,
+					vec->device.bytes, cudaMemcpyHostToDevice,
+					ctx_stream(vec->ctx)));
+		/* the staging buffer goes back to the cache: finish the copy first */
+		CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
+	}
+	pinned_release(vec->ctx, vec->host.ptr);
+	vec->host.ptr = NULL;
+	vec->host.bytes = 0;
+}
+
+extern "C" void vkhel_vector_dbgprint(const struct vkhel_vector *vec) {
+	uint64_t *mapped = NULL;
+	vkhel_vector_map((struct vkhel_vector *) vec, (void **) &mapped,
+			vec->length * sizeof(uint64_t));
+	for (size_t i = 0; i < vec->length; i++) {
+		printf(i + 1 == vec->length ? "%" PRIu64 : "%" PRIu64 ", ",
+				mapped[i]);
+	}
+	printf("\n");
+	vkhel_vector_unmap((struct vkhel_vector *) vec);
+}
+
+extern "C" uint64_t vkhel_vector_length(const struct vkhel_vector *vec) {
+	return vec->length;
+}
+
+extern "C" void *vkhel_vector_device_ptr(struct vkhel_vector *vec) {
+	return vec->device.ptr;
+}
+
+extern "C" void vkhel_vector_upload(struct vkhel_vector *vec,
+		const uint64_t *src, uint64_t offset, uint64_t count) {
+	VK_REQUIRE(offset + count <= vec->length, "upload out of range");
+	enter(vec->ctx);
+	if (count) {
+		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec) + offset, src,
+					count * sizeof(uint64_t), cudaMemcpyHostToDevice,
+					ctx_stream(vec->ctx)));
+	}
+}
+
+extern "C" void vkhel_vector_download(const struct vkhel_vector *vec,
+		uint64_t *dst, uint64_t offset, uint64_t count) {
+	VK_REQUIRE(offset + count <= vec->length, "download out of range");
+	enter(vec->ctx);
+	if (count) {
+		CUDA_CHECK(cudaMemcpyAsync(dst, dev_u64(vec) + offset,
+					count * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+					ctx_stream(vec->ctx)));
+	}
+}
+
+/* ---- debug tracing (reference: VKHEL_DEBUG blocks, e.g. vector.c:305-314) --- */
+#ifdef VKHEL_DEBUG
+#define DBG_VEC(label, v) do { printf("\t%s: ", label); \
+		vkhel_vector_dbgprint(v); } while (0)
+#define DBG(...) printf(__VA_ARGS__)
+#else
+#define DBG_VEC(label, v) do { } while (0)
+#define DBG(...) do { } while (0)
+#endif
+
+/* ---- element-wise entry points ------------------------------------------------
+ * As in the reference every op runs over result->length elements and operand
+ * lengths are not checked (src/kernels/elemmul.c:164,173-174). */
+extern "C" void vkhel_vector_elemfma(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result, uint64_t multiplier, uint64_t mod) {
+	VK_REQUIRE(a->ctx == b->ctx && b->ctx == result->ctx,
+			"elemfma: vectors belong to different contexts");
+	VK_REQUIRE(mod >= 2, "elemfma: modulus must be at least 2");
+	enter(result->ctx);
+	DBG("elemfma (multiplier: %" PRIu64 " mod: %" PRIu64 ")\n",
+			multiplier, mod);
+	DBG_VEC("a", a);
+	DBG_VEC("b", b);
+	launch_elemfma(result->ctx, dev_u64(a), dev_u64(b), dev_u64(result),
+			result->length, multiplier, mod);
+	DBG_VEC("result", result);
+}
+
+extern "C" void vkhel_vector_elemmul(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result, uint64_t mod) {
+	VK_REQUIRE(a->ctx == b->ctx && b->ctx == result->ctx,
+			"elemmul: vectors belong to different contexts");
+	VK_REQUIRE(mod >= 2, "elemmul: modulus must be at least 2");
+	enter(result->ctx);
+	DBG("elemmul mod: %" PRIu64 "\n", mod);
+	DBG_VEC("a", a);
+	DBG_VEC("b", b);
+	launch_elemmul(result->ctx, dev_u64(a), dev_u64(b), dev_u64(result),
+			result->length, mod);
+	DBG_VEC("result", result);
+}
+
+extern "C" void vkhel_vector_elemmul_rns(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result, const uint64_t *mods,
+		uint64_t limbs, uint64_t n, uint64_t batch) {
+	VK_REQUIRE(a->ctx == b->ctx && b->ctx == result->ctx,
+			"elemmul_rns: vectors belong to different contexts");
+	const uint64_t total = limbs * n * batch;
+	VK_REQUIRE(a->length >= total && b->length >= total
+			&& result->length >= total, "elemmul_rns: vector too short");
+	VK_REQUIRE(limbs >= 1 && limbs <= 64, "elemmul_rns: 1..64 limbs");
+	enter(result->ctx);
+	launch_elemmul_rns(result->ctx, dev_u64(a), dev_u64(b), dev_u64(result),
+			mods, limbs, n, batch);
+}
+
+extern "C" void vkhel_vector_elemgtadd(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, uint64_t bound, uint64_t diff) {
+	VK_REQUIRE(operand->ctx == result->ctx,
+			"elemgtadd: vectors belong to different contexts");
+	enter(result->ctx);
+	launch_elemgtadd(result->ctx, dev_u64(operand), dev_u64(result),
+			result->length, bound, diff);
+}
+
+extern "C" void vkhel_vector_elemgtsub(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, uint64_t bound, uint64_t diff,
+		uint64_t mod) {
+	VK_REQUIRE(operand->ctx == result->ctx,
+			"elemgtsub: vectors belong to different contexts");
+	VK_REQUIRE(mod >= 2, "elemgtsub: modulus must be at least 2");
+	enter(result->ctx);
+	launch_elemgtsub(result->ctx, dev_u64(operand), dev_u64(result),
+			result->length, bound, diff, mod);
+}
+
+extern "C" void vkhel_vector_elemmod(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, uint64_t mod, uint64_t q) {
+	VK_REQUIRE(operand->ctx == result->ctx,
+			"elemmod: vectors belong to different contexts");
+	VK_REQUIRE(mod >= 2, "elemmod: modulus must be at least 2");
+	enter(result->ctx);
+	DBG("elemmod mod: %" PRIu64 ", q: %" PRIu64 "\n", mod, q);
+	/* dispatch rule of the reference, src/vector.c:360-368 */
+	if (mod == 2) {
+		launch_elemmodbytwo(result->ctx, dev_u64(operand), dev_u64(result),
+				result->length, q / 2);
+	} else {
+		launch_elemgtsub(result->ctx, dev_u64(operand), dev_u64(result),
+				result->length, q / 2, q, mod);
+	}
+}
+
+/* ---- transforms ------------------------------------------------------------------ */
+static void check_ntt(const char *what, const struct vkhel_vector *operand,
+		const struct vkhel_vector *result, const struct vkhel_ntt_tables *ntt,
+		uint64_t count) {
+	VK_REQUIRE(operand->ctx == result->ctx,
+			"%s: vectors belong to different contexts", what);
+	VK_REQUIRE(ntt, "%s: NULL tables", what);
+	VK_REQUIRE(operand->length >= count && result->length >= count,
+			"%s: vector shorter than the transform (%" PRIu64 ")", what,
+			count);
+}
+
+extern "C" void vkhel_vector_forward_transform_batch(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt, uint64_t batch) {
+	check_ntt("forward_transform", operand, result, ntt, ntt->n * batch);
+	struct vkhel_ctx *ctx = result->ctx;
+	enter(ctx);
+	if (ntt->n < 2 || batch == 0) {
+		return; /* no stages: the reference leaves result untouched */
+	}
+	launch_ntt(ctx, false, dev_u64(operand), dev_u64(result),
+			ntt_tables_device_desc(ctx, ntt), 1, batch,
+			(unsigned) ntt->log2n, ntt->q);
+}
+
+extern "C" void vkhel_vector_inverse_transform_batch(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt, uint64_t batch) {
+	check_ntt("inverse_transform", operand, result, ntt, ntt->n * batch);
+	struct vkhel_ctx *ctx = result->ctx;
+	enter(ctx);
+	if (batch == 0) {
+		return;
+	}
+	if (ntt->n < 2) {
+		/* no butterfly stage; the reference still multiplies result (not
+		 * operand) by n^-1 = 1, i.e. reduces it (vector.c:633-639) */
+		launch_elemmulconst(ctx, dev_u64(result), dev_u64(result), batch,
+				ntt->inv_n, ntt->q);
+		return;
+	}
+	launch_ntt(ctx, true, dev_u64(operand), dev_u64(result),
+			ntt_tables_device_desc(ctx, ntt), 1, batch,
+			(unsigned) ntt->log2n, ntt->q);
+}
+
+extern "C" void vkhel_vector_forward_transform(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt) {
+	DBG("forward transform (degree: %" PRIu64 " mod: %" PRIu64
+			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
+	DBG_VEC("operand", operand);
+	vkhel_vector_forward_transform_batch(operand, result, ntt, 1);
+	DBG_VEC("result", result);
+}
+
+extern "C" void vkhel_vector_inverse_transform(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *ntt) {
+	DBG("inverse transform (degree: %" PRIu64 " mod: %" PRIu64
+			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
+	DBG_VEC("operand", operand);
+	vkhel_vector_inverse_transform_batch(operand, result, ntt, 1);
+	/* The reference scales every element of result, not just the first n
+	 * (vector.c:635-638 run elemmulconst over result->length).
+	 * The n^-1 factor of the first n is folded into the last butterfly
+	 * stage; the tail gets the same Shoup multiplication here. */
+	if (result->length > ntt->n) {
+		launch_elemmulconst(result->ctx, dev_u64(result) + ntt->n,
+				dev_u64(result) + ntt->n, result->length - ntt->n,
+				ntt->inv_n, ntt->q);
+	}
+	DBG_VEC("result", result);
+}
+
+static const limb_desc *rns_prepare(const char *what,
+		const struct vkhel_vector *operand, const struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch,
+		uint64_t *q_max) {
+	VK_REQUIRE(ntt && limbs >= 1, "%s: need at least one limb", what);
+	check_ntt(what, operand, result, ntt[0], ntt[0]->n * limbs * batch);
+	*q_max = 0;
+	for (uint64_t l = 0; l < limbs; l++) {
+		if (ntt[l]->q > *q_max) {
+			*q_max = ntt[l]->q;
+		}
+	}
+	return rns_plan_device_descs(result->ctx, ntt, limbs);
+}
+
+extern "C" void vkhel_vector_forward_transform_rns(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch) {
+	uint64_t q_max;
+	enter(result->ctx);
+	const limb_desc *descs = rns_prepare("forward_transform_rns", operand,
+			result, ntt, limbs, batch, &q_max);
+	if (ntt[0]->n < 2 || batch == 0) {
+		return;
+	}
+	launch_ntt(result->ctx, false, dev_u64(operand), dev_u64(result), descs,
+			limbs, limbs * batch, (unsigned) ntt[0]->log2n, q_max);
+}
+
+extern "C" void vkhel_vector_inverse_transform_rns(
+		const struct vkhel_vector *operand, struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch) {
+	uint64_t q_max;
+	enter(result->ctx);
+	const limb_desc *descs = rns_prepare("inverse_transform_rns", operand,
+			result, ntt, limbs, batch, &q_max);
+	VK_REQUIRE(ntt[0]->n >= 2, "inverse_transform_rns: n must be at least 2");
+	if (batch == 0) {
+		return;
+	}
+	launch_ntt(result->ctx, true, dev_u64(operand), dev_u64(result), descs,
+			limbs, limbs * batch, (unsigned) ntt[0]->log2n, q_max);
+}
+
+extern "C" void vkhel_vector_polymul_rns(
+		const struct vkhel_vector *a, const struct vkhel_vector *b,
+		struct vkhel_vector *result,
+		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch) {
+	uint64_t q_max;
+	struct vkhel_ctx *ctx = result->ctx;
+	enter(ctx);
+	VK_REQUIRE(a->ctx == ctx && b->ctx == ctx,
+			"polymul_rns: vectors belong to different contexts");
+	const limb_desc *descs = rns_prepare("polymul_rns", a, result, ntt, limbs,
+			batch, &q_max);
+	const uint64_t n = ntt[0]->n;
+	const uint64_t total = n * limbs * batch;
+	VK_REQUIRE(b->length >= total, "polymul_rns: vector b too short");
+	VK_REQUIRE(n >= 2 && limbs <= 64, "polymul_rns: n >= 2, at most 64 limbs");
+	if (batch == 0) {
+		return;
+	}
+	/* unfused sequence of the reference API: NTT(a) -> result,
+	 * NTT(b) -> scratch, product, inverse */
+	u64 *tmp = (u64 *) device_scratch(ctx, total * sizeof(u64));
+	uint64_t mods[64];
+	for (uint64_t l = 0; l < limbs; l++) {
+		mods[l] = ntt[l]->q;
+	}
+	const unsigned log2n = (unsigned) ntt[0]->log2n;
+	launch_ntt(ctx, false, dev_u64(a), dev_u64(result), descs, limbs,
+			limbs * batch, log2n, q_max);
+	launch_ntt(ctx, false, dev_u64(b), tmp, descs, limbs, limbs * batch,
+			log2n, q_max);
+	launch_elemmul_rns(ctx, dev_u64(result), tmp, dev_u64(result), mods,
+			limbs, n, batch);
+	launch_ntt(ctx, true, dev_u64(result), dev_u64(result), descs, limbs,
+			limbs * batch, log2n, q_max);
+}
