@@ -10,7 +10,8 @@
 #   make check      run all reference programs (needs a GPU)
 
 NVCC      ?= /usr/local/cuda/bin/nvcc
-CC        ?= gcc
+# (the image exports CC=/opt/gcc/bin/gcc, a wrapper; use the system gcc)
+HOSTCC    ?= /usr/bin/gcc
 REF       ?= /root/reference
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 INC       := -Iinclude -Iinclude/vkhel -Ivkhel_b200/csrc
@@ -51,7 +52,7 @@ $(OBJ_DIR)/%.o: $(SRC_DIR)/%.cu $(HDRS)
 
 $(OBJ_DIR)/%.o: $(SRC_DIR)/%.c $(HDRS)
 	@mkdir -p $(OBJ_DIR)
-	$(CC) $(CFLAGS) -c $< -o $@
+	$(HOSTCC) $(CFLAGS) -c $< -o $@
 
 $(STATIC): $(OBJS)
 	@mkdir -p $(LIB_DIR)
@@ -67,11 +68,11 @@ $(SHARED): $(OBJS) vkhel.syms
 # (include path = include/ and include/vkhel/, as in meson.build:31-32)
 $(BIN_DIR)/ref_example: $(REF)/examples/example.c $(SHARED)
 	@mkdir -p $(BIN_DIR)
-	$(CC) -O2 $(INC) $< -o $@ -L$(LIB_DIR) -lvkhel -Wl,-rpath,'$$ORIGIN/../../$(LIB_DIR)'
+	$(HOSTCC) -O2 $(INC) $< -o $@ -L$(LIB_DIR) -lvkhel -Wl,-rpath,'$$ORIGIN/../../$(LIB_DIR)'
 
 $(BIN_DIR)/ref_test_%: $(REF)/test/%.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
-	$(CC) -O2 $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+	$(HOSTCC) -O2 $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 
 oracle:
 	$(MAKE) -C oracle REF=$(REF)

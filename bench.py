@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""Benchmark of the NTT hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): 64-bit NTTs/sec at n=2^16.  Workload: the CKKS-like
+shape of BASELINE configs[2] -- n = 2^16, 32 RNS limbs (the 32 largest primes
+below 2^60 with q = 1 mod 2^18) x batch 16 = 512 polynomials = 256 MiB per
+GPU.  One step = one forward transform of the whole batch followed by one
+inverse transform of it (1024 NTTs).  With N GPUs every rank runs that
+workload on its own batch shard (weak scaling, no data-path collective; the
+reference has no multi-device path at all).
+
+One JSON line is printed by rank 0.  `value` is measured with the inputs
+resident in HBM; `e2e` is the same metric through the C-ABI with host buffers
+(pinned host -> device copy of the step's input and device -> host copy of its
+result inside the timed region).  `roofline` places the step against the HBM
+roofline with the algorithmic 16*n bytes per NTT; `cpu_baseline` is the CPU
+oracle (a port of the reference's arithmetic; the reference has no CPU NTT of
+its own) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2N = 16
+N = 1 << LOG2N
+LIMBS = 32
+BATCH = 16
+POLYS = LIMBS * BATCH
+METRIC = "64-bit NTTs/sec at n=2^16"
+WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
+            "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
+            "step = forward + inverse of the whole batch")
+
+
+# ---- clocks --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device),
+                 "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                    "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- workload ------------------------------------------------------------------------
+def make_inputs(primes, seed):
+    from vkhel_b200 import params
+    out = np.empty(POLYS * N, np.uint64)
+    for p in range(POLYS):
+        q = primes[p % LIMBS]
+        out[p * N:(p + 1) * N] = params.xorshift64_stream(
+            0x9E3779B97F4A7C15 + seed * 1000 + p, N, q)
+    return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU arm -------------------------------------------------------------------------
+def cpu_arm(primes, psis, target_seconds, sample_polys=None):
+    """fwd+inv on a bounded sample with the CPU oracle on all host cores.
+    Returns (ntts_per_sec, cores, sample description, seconds)."""
+    import oracle
+    cores = os.cpu_count() or 1
+    limbs = min(LIMBS, 4)
+    tables = [oracle.Tables(N, primes[l], psis[l]) for l in range(limbs)]
+    from vkhel_b200 import params
+    one = params.xorshift64_stream(1, N, primes[0])
+    t0 = time.perf_counter()
+    oracle.inverse(oracle.forward(one, tables[0]), tables[0])
+    t_one = time.perf_counter() - t0            # 2 NTTs, single thread
+    if sample_polys is None:
+        sample_polys = int(max(cores, min(POLYS, cores * target_seconds / t_one)))
+        sample_polys -= sample_polys % limbs or 0
+        sample_polys = max(sample_polys, limbs)
+    x = np.concatenate([params.xorshift64_stream(100 + p, N, primes[p % limbs])
+                        for p in range(sample_polys)])
+    t0 = time.perf_counter()
+    fwd = oracle.forward_batch(x, tables, threads=cores)
+    back = oracle.inverse_batch(fwd, tables, threads=cores)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(back, x)
+    sample = ("%d polys of n=2^16 over %d limbs, forward+inverse, "
+              "OpenMP over polynomials" % (sample_polys, limbs))
+    return 2 * sample_polys / dt, cores, sample, dt, (tables, x)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU arithmetic (the oracle port: the
+    reference's transform exists only as GLSL and no Vulkan stack is in this
+    image) on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vkhel_b200 import params
+    import oracle
+    primes = params.ntt_primes(LIMBS)
+    psis = [params.find_psi(N, q) for q in primes[:4]]
+    cores = os.cpu_count() or 1
+    rate, cores, sample, dt, (tables, x) = cpu_arm(primes, psis, 2.0)
+    sample_polys = x.size // N
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle.inverse_batch(oracle.forward_batch(x, tables, threads=cores),
+                             tables, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.inverse_batch(oracle.forward_batch(x, tables, threads=cores),
+                             tables, threads=cores)
+    elapsed = time.perf_counter() - t0
+    value = 2 * sample_polys * args.steps / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value,
+        "unit": "NTT/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "sample": sample + " per step"},
+        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": cores,
+                         "kind": "port", "sample": sample + " per step"},
+        "e2e": {"value": value, "unit": "NTT/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- GPU arm -------------------------------------------------------------------------
+def run_native_arm(args):
+    import vkhel_b200 as vk
+    from vkhel_b200 import params
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl",
+                                device_id=torch.device("cuda", local_rank))
+
+    if vk.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; vkhel has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(value):
+        if dist is None:
+            return value
+        import torch
+        t = torch.tensor([value], dtype=torch.float64,
+                         device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    primes = params.ntt_primes(LIMBS)
+    psis = [params.find_psi(N, q) for q in primes]
+    ctx = vk.Context(local_rank)
+    tables = [vk.NttTables(N, q, w) for q, w in zip(primes, psis)]
+
+    host_in = vk.host_alloc(POLYS * N)
+    host_out = vk.host_alloc(POLYS * N)
+    host_in.array[:] = make_inputs(primes, rank)
+    data = ctx.vector(POLYS * N, zero=False)
+    work = ctx.vector(POLYS * N, zero=False)
+    data.upload(host_in)
+    ctx.sync()
+
+    def step_resident():
+        ctx.forward_transform_rns(data, work, tables, BATCH)
+        ctx.inverse_transform_rns(work, work, tables, BATCH)
+
+    def step_e2e():
+        data.upload(host_in)
+        ctx.forward_transform_rns(data, work, tables, BATCH)
+        ctx.inverse_transform_rns(work, work, tables, BATCH)
+        work.download(host_out)
+
+    timer = ctx.timer()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        ctx.sync()
+        barrier()
+        l0 = ctx.launch_count
+        timer.start()
+        for _ in range(steps):
+            step_fn()
+        timer.stop()
+        ms = timer.elapsed_ms()
+        ctx.sync()
+        barrier()
+        return max_over_ranks(ms), ctx.launch_count - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # correctness of what was just timed: the round trip returns the input
+    work.download(host_out)
+    ctx.sync()
+    ok = bool(np.array_equal(host_out.array, host_in.array))
+
+    # forward-only and inverse-only durations (per direction roofline)
+    def fwd_only():
+        ctx.forward_transform_rns(data, work, tables, BATCH)
+
+    def inv_only():
+        ctx.inverse_transform_rns(work, work, tables, BATCH)
+
+    ms_fwd, _ = timed(fwd_only, args.steps, 1)
+    ms_inv, _ = timed(inv_only, args.steps, 1)
+
+    ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 10)), 1)
+    e2e_steps = max(2, min(args.steps, 10))
+    ok = ok and bool(np.array_equal(host_out.array, host_in.array))
+
+    ntts_per_step = 2 * POLYS
+    ms_per_step = ms_total / args.steps
+    value = world * ntts_per_step / (ms_per_step * 1e-3)
+    e2e_value = world * ntts_per_step / (ms_e2e / e2e_steps * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        algo_bytes = 16 * N * ntts_per_step
+        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "NTT/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "n": N, "limbs": LIMBS,
+                "batch_per_gpu": BATCH, "parallelism": "batch-sharded x%d, "
+                "no collective" % world,
+                "l2": "working set 512 MiB per step > 126 MB L2, no flush",
+                "round_trip_exact": ok,
+            },
+            "e2e": {"value": e2e_value, "unit": "NTT/s",
+                    "h2d_bytes_per_step": POLYS * N * 8,
+                    "d2h_bytes_per_step": POLYS * N * 8,
+                    "steps": e2e_steps,
+                    "path": "vkhel_vector_upload (pinned) -> "
+                            "forward_transform_rns -> inverse_transform_rns "
+                            "-> vkhel_vector_download, one stream"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src,
+                "kernel": "whole step (forward + inverse NTT, all passes)",
+                "algorithmic_bytes_per_step": algo_bytes,
+                "forward_ms": ms_fwd / args.steps,
+                "inverse_ms": ms_inv / args.steps,
+                "forward_GBps": 16 * N * POLYS / (ms_fwd / args.steps * 1e-3) / 1e9,
+                "inverse_GBps": 16 * N * POLYS / (ms_inv / args.steps * 1e-3) / 1e9,
+            },
+        }
+        if world == 1 and not args.no_cpu:
+            rate, cores, sample, dt, _ = cpu_arm(primes, psis[:4], 12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "NTT/s",
+                                    "cores": cores, "kind": "port",
+                                    "sample": sample, "seconds": dt}
+        print(json.dumps(line))
+
+    timer.destroy()
+    for v in (data, work):
+        v.destroy()
+    for t in tables:
+        t.destroy()
+    host_in.free()
+    host_out.free()
+    ctx.destroy()
+    if dist is not None:
+        dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: round trip mismatch -- result invalid")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu", action="store_true",
+                    help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,33 @@
+"""GPU suite: the reference's own programs, compiled UNMODIFIED from
+/root/reference (examples/example.c, test/vector.c, test/ntt.c,
+test/numbers.c) against include/ and this library by the Makefile, must run
+to completion: that is the drop-in claim of the C API."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "build", "bin")
+
+
+@pytest.mark.parametrize("name", ["ref_test_vector", "ref_example",
+                                  "ref_test_ntt", "ref_test_numbers"])
+def test_reference_program(name):
+    path = os.path.join(BIN, name)
+    if not os.path.exists(path):
+        pytest.fail("%s missing: run `make` where /root/reference exists; "
+                    "the binary travels to the GPU box" % path)
+    res = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    if name == "ref_test_vector":
+        for t in ("copy_from_host", "dup", "elemfma", "elemmod", "elemmul",
+                  "elemgtadd", "elemgtsub", "forward_transform",
+                  "inverse_transform", "forward_transform_big",
+                  "inverse_transform_big"):
+            assert "%s passed" % t in res.stdout
+    if name == "ref_example":
+        assert res.stdout.count("{4, 0, 0, 4, }") == 2

@@ -1,0 +1,315 @@
+"""ctypes binding of libvkhel.so -- the reference-side stub a maintainer would
+write for a Python caller.  Every method is a direct call
+of the C entry point of the same name (include/vkhel/vkhel.h,
+include/vkhel/vkhel_ext.h)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "lib", "libvkhel.so")
+
+_u64 = ctypes.c_uint64
+_p64 = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+
+
+def build():
+    """Compile the library in-tree (nvcc, sm_100a)."""
+    subprocess.check_call(["make", "-C", _ROOT, "-s", "-j8", "libs"])
+
+
+# name -> (restype, argtypes); the 18 reference entry points first
+SIGNATURES = {
+    "vkhel_ctx_create": (_vp, []),
+    "vkhel_ctx_destroy": (None, [_vp]),
+    "vkhel_ntt_tables_create": (_vp, [_u64, _u64, _u64]),
+    "vkhel_ntt_tables_destroy": (None, [_vp]),
+    "vkhel_vector_create": (_vp, [_vp, _u64]),
+    "vkhel_vector_create2": (_vp, [_vp, _u64, ctypes.c_bool]),
+    "vkhel_vector_destroy": (None, [_vp]),
+    "vkhel_vector_dup": (_vp, [_vp]),
+    "vkhel_vector_copy_from_host": (None, [_vp, _p64]),
+    "vkhel_vector_map": (None, [_vp, ctypes.POINTER(_vp), ctypes.c_size_t]),
+    "vkhel_vector_unmap": (None, [_vp]),
+    "vkhel_vector_elemfma": (None, [_vp, _vp, _vp, _u64, _u64]),
+    "vkhel_vector_elemmod": (None, [_vp, _vp, _u64, _u64]),
+    "vkhel_vector_elemmul": (None, [_vp, _vp, _vp, _u64]),
+    "vkhel_vector_elemgtadd": (None, [_vp, _vp, _u64, _u64]),
+    "vkhel_vector_elemgtsub": (None, [_vp, _vp, _u64, _u64, _u64]),
+    "vkhel_vector_forward_transform": (None, [_vp, _vp, _vp]),
+    "vkhel_vector_inverse_transform": (None, [_vp, _vp, _vp]),
+    # private-header symbols that match the export glob
+    "vkhel_vector_dbgprint": (None, [_vp]),
+    "vkhel_ntt_tables_dbgprint": (None, [_vp]),
+    # extensions (vkhel_ext.h)
+    "vkhel_device_count": (ctypes.c_int, []),
+    "vkhel_ctx_create_device": (_vp, [ctypes.c_int]),
+    "vkhel_ctx_device": (ctypes.c_int, [_vp]),
+    "vkhel_ctx_sync": (None, [_vp]),
+    "vkhel_ctx_stream": (_vp, [_vp]),
+    "vkhel_host_alloc": (_vp, [ctypes.c_size_t]),
+    "vkhel_host_free": (None, [_vp]),
+    "vkhel_vector_length": (_u64, [_vp]),
+    "vkhel_vector_device_ptr": (_vp, [_vp]),
+    "vkhel_vector_upload": (None, [_vp, _vp, _u64, _u64]),
+    "vkhel_vector_download": (None, [_vp, _vp, _u64, _u64]),
+    "vkhel_vector_forward_transform_batch": (None, [_vp, _vp, _vp, _u64]),
+    "vkhel_vector_inverse_transform_batch": (None, [_vp, _vp, _vp, _u64]),
+    "vkhel_vector_forward_transform_rns": (None, [_vp, _vp,
+                                                  ctypes.POINTER(_vp), _u64,
+                                                  _u64]),
+    "vkhel_vector_inverse_transform_rns": (None, [_vp, _vp,
+                                                  ctypes.POINTER(_vp), _u64,
+                                                  _u64]),
+    "vkhel_vector_elemmul_rns": (None, [_vp, _vp, _vp, _p64, _u64, _u64,
+                                        _u64]),
+    "vkhel_vector_polymul_rns": (None, [_vp, _vp, _vp, ctypes.POINTER(_vp),
+                                        _u64, _u64]),
+    "vkhel_timer_create": (_vp, [_vp]),
+    "vkhel_timer_start": (None, [_vp]),
+    "vkhel_timer_stop": (None, [_vp]),
+    "vkhel_timer_elapsed_ms": (ctypes.c_double, [_vp]),
+    "vkhel_timer_destroy": (None, [_vp]),
+    "vkhel_ctx_launch_count": (_u64, [_vp]),
+    "vkhel_ctx_flush_l2": (None, [_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libvkhel.so is not built (%s): run `make` or "
+                "__graft_entry__.build(); there is no CPU fallback" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def device_count():
+    return lib().vkhel_device_count()
+
+
+def _as_u64(x):
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from vkhel_host_alloc."""
+
+    def __init__(self, count):
+        self.count = count
+        self.ptr = lib().vkhel_host_alloc(count * 8)
+        buf = (ctypes.c_uint64 * count).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint64)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().vkhel_host_free(self.ptr)
+            self.ptr = None
+
+
+def host_alloc(count):
+    return PinnedArray(count)
+
+
+class NttTables:
+    """struct vkhel_ntt_tables (vkhel_ntt_tables_create / _destroy)"""
+
+    def __init__(self, n, q, w):
+        self.n, self.q, self.w = n, q, w
+        self.handle = lib().vkhel_ntt_tables_create(n, q, w)
+
+    def _field(self, index):
+        # struct layout of include/priv/ntt_tables.h: n, q, w, then 4 pointers
+        raw = ctypes.cast(self.handle, ctypes.POINTER(ctypes.c_uint64))
+        addr = raw[3 + index]
+        arr = (ctypes.c_uint64 * self.n).from_address(addr)
+        return np.frombuffer(arr, dtype=np.uint64).copy()
+
+    roots_of_unity = property(lambda self: self._field(0))
+    inv_roots_of_unity = property(lambda self: self._field(1))
+    roots_barrett_factors = property(lambda self: self._field(2))
+    inv_roots_barrett_factors = property(lambda self: self._field(3))
+
+    def destroy(self):
+        if self.handle:
+            lib().vkhel_ntt_tables_destroy(self.handle)
+            self.handle = None
+
+
+def _table_array(tables):
+    return (_vp * len(tables))(*[t.handle for t in tables])
+
+
+class Vector:
+    """struct vkhel_vector"""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    @property
+    def length(self):
+        return int(lib().vkhel_vector_length(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            lib().vkhel_vector_destroy(self.handle)
+            self.handle = None
+
+    def dup(self):
+        return Vector(self.ctx, lib().vkhel_vector_dup(self.handle))
+
+    def copy_from_host(self, data):
+        data = _as_u64(data)
+        assert data.size >= self.length
+        lib().vkhel_vector_copy_from_host(
+            self.handle, data.ctypes.data_as(_p64))
+
+    def to_host(self):
+        """map + copy + unmap, the reference's way to read a vector"""
+        mem = _vp()
+        n = self.length
+        lib().vkhel_vector_map(self.handle, ctypes.byref(mem), n * 8)
+        if n:
+            buf = (ctypes.c_uint64 * n).from_address(mem.value)
+            out = np.frombuffer(buf, dtype=np.uint64).copy()
+        else:
+            out = np.empty(0, np.uint64)
+        lib().vkhel_vector_unmap(self.handle)
+        return out
+
+    def upload(self, pinned, offset=0, count=None):
+        count = pinned.count if count is None else count
+        lib().vkhel_vector_upload(self.handle, pinned.ptr, offset, count)
+
+    def download(self, pinned, offset=0, count=None):
+        count = pinned.count if count is None else count
+        lib().vkhel_vector_download(self.handle, pinned.ptr, offset, count)
+
+
+class Context:
+    """struct vkhel_ctx; methods are the vkhel_vector_* operators"""
+
+    def __init__(self, device=None):
+        if device is None:
+            self.handle = lib().vkhel_ctx_create()
+        else:
+            self.handle = lib().vkhel_ctx_create_device(device)
+
+    def destroy(self):
+        if self.handle:
+            lib().vkhel_ctx_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        lib().vkhel_ctx_sync(self.handle)
+
+    def flush_l2(self):
+        lib().vkhel_ctx_flush_l2(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(lib().vkhel_ctx_launch_count(self.handle))
+
+    def vector(self, length, zero=True):
+        return Vector(self, lib().vkhel_vector_create2(self.handle, length,
+                                                       zero))
+
+    def from_host(self, data):
+        data = _as_u64(data)
+        v = self.vector(data.size, zero=False)
+        v.copy_from_host(data)
+        return v
+
+    # element-wise
+    def elemfma(self, a, b, result, multiplier, mod):
+        lib().vkhel_vector_elemfma(a.handle, b.handle, result.handle,
+                                   multiplier, mod)
+
+    def elemmod(self, a, result, mod, q):
+        lib().vkhel_vector_elemmod(a.handle, result.handle, mod, q)
+
+    def elemmul(self, a, b, result, mod):
+        lib().vkhel_vector_elemmul(a.handle, b.handle, result.handle, mod)
+
+    def elemgtadd(self, a, result, bound, diff):
+        lib().vkhel_vector_elemgtadd(a.handle, result.handle, bound, diff)
+
+    def elemgtsub(self, a, result, bound, diff, mod):
+        lib().vkhel_vector_elemgtsub(a.handle, result.handle, bound, diff, mod)
+
+    def elemmul_rns(self, a, b, result, mods, n, batch):
+        mods = _as_u64(mods)
+        lib().vkhel_vector_elemmul_rns(a.handle, b.handle, result.handle,
+                                       mods.ctypes.data_as(_p64), mods.size,
+                                       n, batch)
+
+    # transforms
+    def forward_transform(self, operand, result, ntt):
+        lib().vkhel_vector_forward_transform(operand.handle, result.handle,
+                                             ntt.handle)
+
+    def inverse_transform(self, operand, result, ntt):
+        lib().vkhel_vector_inverse_transform(operand.handle, result.handle,
+                                             ntt.handle)
+
+    def forward_transform_batch(self, operand, result, ntt, batch):
+        lib().vkhel_vector_forward_transform_batch(
+            operand.handle, result.handle, ntt.handle, batch)
+
+    def inverse_transform_batch(self, operand, result, ntt, batch):
+        lib().vkhel_vector_inverse_transform_batch(
+            operand.handle, result.handle, ntt.handle, batch)
+
+    def forward_transform_rns(self, operand, result, tables, batch):
+        lib().vkhel_vector_forward_transform_rns(
+            operand.handle, result.handle, _table_array(tables), len(tables),
+            batch)
+
+    def inverse_transform_rns(self, operand, result, tables, batch):
+        lib().vkhel_vector_inverse_transform_rns(
+            operand.handle, result.handle, _table_array(tables), len(tables),
+            batch)
+
+    def polymul_rns(self, a, b, result, tables, batch):
+        lib().vkhel_vector_polymul_rns(
+            a.handle, b.handle, result.handle, _table_array(tables),
+            len(tables), batch)
+
+    # timing
+    def timer(self):
+        return Timer(self)
+
+
+class Timer:
+    def __init__(self, ctx):
+        self.handle = lib().vkhel_timer_create(ctx.handle)
+
+    def start(self):
+        lib().vkhel_timer_start(self.handle)
+
+    def stop(self):
+        lib().vkhel_timer_stop(self.handle)
+
+    def elapsed_ms(self):
+        return float(lib().vkhel_timer_elapsed_ms(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            lib().vkhel_timer_destroy(self.handle)
+            self.handle = None
