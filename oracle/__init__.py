@@ -105,8 +105,31 @@ class Tables:
         self.inv_roots = np.empty(n, np.uint64)
         self.roots_shoup = np.empty(n, np.uint64)
         self.inv_roots_shoup = np.empty(n, np.uint64)
-        _lib.oracle_tables(n, q, w, _ptr(self.roots), _ptr(self.inv_roots),
-                           _ptr(self.roots_shoup), _ptr(self.inv_roots_shoup))
+        if q >> 62:
+            # The reference's host Barrett (numbers.c:5-28) shifts the high
+            # product word by 66 - bits(q) and overflows for 63-bit moduli:
+            # its tables are not well defined there.  For such moduli the
+            # oracle states the table CONTRACT with Python
+            # integers instead of restating the broken arithmetic.
+            self._fill_exact()
+        else:
+            _lib.oracle_tables(n, q, w, _ptr(self.roots),
+                               _ptr(self.inv_roots), _ptr(self.roots_shoup),
+                               _ptr(self.inv_roots_shoup))
+
+    def _fill_exact(self):
+        n, q, w = self.n, self.q, self.w
+        bits = n.bit_length() - 1
+        w_inv = pow(w, -1, q) if n > 1 else 1
+        p = pi = 1
+        for i in range(n):
+            idx = int(format(i, "0%db" % bits)[::-1], 2) if bits else 0
+            self.roots[idx] = p
+            self.inv_roots[idx] = pi
+            self.roots_shoup[idx] = (p << 64) // q
+            self.inv_roots_shoup[idx] = (pi << 64) // q
+            p = p * w % q
+            pi = pi * w_inv % q
 
 
 # ---- transforms -----------------------------------------------------------------

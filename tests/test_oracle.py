@@ -231,3 +231,40 @@ def test_batch_driver_matches_single():
                               oracle.forward(x[p * n:(p + 1) * n],
                                              tables[p % 3]))
     assert np.array_equal(oracle.inverse_batch(fwd, tables, threads=2), x)
+
+
+def test_reference_host_barrett_limit():
+    """Domain of the reference: its host Barrett (numbers.c:5-28) is exact up
+    to 62-bit moduli and overflows for 63-bit ones, so its tables are only
+    defined for q < 2^62.  Above that the oracle states the contract instead
+    (oracle.Tables._fill_exact) -- checked here to coincide with the literal
+    restatement where both are defined."""
+    rng = np.random.default_rng(63)
+    q62 = params.Q62_LAZY_MAX
+    for _ in range(2000):
+        a, b = (int(v) for v in rand_mod(rng, 2, q62))
+        assert oracle.multiply_mod(a, b, q62) == a * b % q62
+    q63 = params.Q63_STRICT
+    wrong = 0
+    for _ in range(2000):
+        a, b = (int(v) for v in rand_mod(rng, 2, q63))
+        wrong += oracle.multiply_mod(a, b, q63) != a * b % q63
+    assert wrong > 0
+    n, q = 128, params.P0
+    w = params.find_psi(n, q)
+    lit = oracle.Tables(n, q, w)
+    exact = oracle.Tables(n, q, w)
+    exact._fill_exact()
+    for f in ("roots", "inv_roots", "roots_shoup", "inv_roots_shoup"):
+        assert np.array_equal(getattr(lit, f), getattr(exact, f))
+    # 63-bit modulus: evaluation identity holds with the contract tables
+    n = 8
+    w = params.find_psi(n, q63)
+    t = oracle.Tables(n, q63, w)
+    x = rand_mod(rng, n, q63)
+    fwd = oracle.forward(x, t)
+    for j in range(n):
+        point = pow(w, 2 * brv(j, 3) + 1, q63)
+        assert int(fwd[j]) == sum(int(c) * pow(point, k, q63)
+                                  for k, c in enumerate(x)) % q63
+    assert np.array_equal(oracle.inverse(fwd, t), x)

@@ -26,6 +26,7 @@
  * inv_root[1] * n^-1).
  */
 #include "common.cuh"
+#include "ntt_engine.cuh"
 
 /* ======================================================================================
  * Generic path: any n >= 2, any batch.  One CTA stages GEN_ELEMS coefficients
@@ -230,6 +231,439 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 }
 
 /* ======================================================================================
+ * Fast path (q < 2^62, n >= 8): register radix-8 engine (ntt_engine.cuh).
+ *
+ *   row pass    : the deepest K_row stages; a tile is 2^K_row CONTIGUOUS
+ *                 coefficients.  One warp-group of 2^(K_row-3) lanes per tile:
+ *                 global -> registers -> (shared-memory exchanges inside the
+ *                 warp, __syncwarp only) -> global.  A CTA stages the twiddle
+ *                 subtrees of its tiles in shared memory once and reuses them
+ *                 over the batch.
+ *   column pass : the K_col stages above them; a tile is 2^K_col coefficients
+ *                 at stride 2^(L-s0-K_col).  A CTA takes C adjacent columns;
+ *                 thread = (column, row group), lanes along the columns, so
+ *                 every global and shared access is contiguous.
+ *
+ * Forward: column pass (stages 0..) then row pass; inverse: row pass then
+ * column pass, whose last stage carries the n^-1 scaling.  Values between the
+ * passes stay lazy ([0,4q) forward, [0,2q) inverse) in the result vector.
+ * ====================================================================================== */
+#define FAST_THREADS 256
+
+struct fast_pass {
+	const u64 *src;
+	u64 *dst;
+	const limb_desc *descs;
+	unsigned limbs;
+	unsigned log2n;
+	unsigned s0;        /* first stage of the pass */
+	u64 polys;          /* batch * limbs */
+	unsigned hgroup_log2; /* row pass: consecutive H per CTA */
+	unsigned bchunk;      /* row pass: batch entries per CTA */
+};
+
+/* padded position of tile element i in a warp-group's exchange buffer: 4 words
+ * of padding per 32 keep the strided reads of the second round conflict-free */
+__device__ __forceinline__ int xpad(int i) {
+	return i + ((i >> 5) << 2);
+}
+
+template <int K>
+struct row_cfg {
+	static constexpr int tile = 1 << K;
+	static constexpr int xbuf = tile + ((tile >> 5) << 2) + 4; /* words per group */
+	static constexpr int group = 1 << (K - 3);                 /* lanes per tile */
+	static constexpr int groups_per_warp = 32 / group;
+	static constexpr int groups_per_cta = (FAST_THREADS / 32) * groups_per_warp;
+};
+
+template <bool INV, int K>
+__global__ void __launch_bounds__(FAST_THREADS)
+ntt_rows_kernel(const fast_pass p) {
+	using G = tile_geom<K>;
+	using C = row_cfg<K>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	const unsigned L = p.log2n, s0 = p.s0;       /* s0 + K == L */
+	const unsigned hgroup = 1u << p.hgroup_log2;
+	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;                 /* [hgroup][2^K] */
+	u64 *sm_x = (u64 *) (sm_tw + ((size_t) hgroup << K));        /* per group */
+
+	/* blockIdx.x -> (batch chunk, limb, H group) */
+	const unsigned hgroups = (1u << s0) >> p.hgroup_log2;
+	unsigned blk = blockIdx.x;
+	const unsigned hg = blk % hgroups;
+	blk /= hgroups;
+	const unsigned limb = blk % p.limbs;
+	const unsigned bc = blk / p.limbs;
+	const u64 batch = p.polys / p.limbs;
+	const u64 b0 = (u64) bc * p.bchunk;
+	const unsigned nb = (unsigned) (batch - b0 < p.bchunk ? batch - b0 : p.bchunk);
+	const unsigned H0 = hg << p.hgroup_log2;
+
+	const limb_desc d = p.descs[limb];
+	const u64 q = d.q, twoq = 2 * d.q;
+	const ulonglong2 *tw_g = d.tw + (INV ? ((u64) 1 << L) : 0);
+
+	/* stage the twiddle subtrees rooted at node 2^s0 + H, H = H0 .. H0+hgroup-1 */
+	for (unsigned v = threadIdx.x; v < (hgroup << K); v += FAST_THREADS) {
+		const unsigned h = v >> K, node = v & ((1u << K) - 1);
+		if (node) {
+			const unsigned u = 31 - __clz(node);
+			const u64 root = ((u64) 1 << s0) + H0 + h;
+			sm_tw[v] = tw_g[(root << u) + (node - (1u << u))];
+		}
+	}
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int t = lane & (C::group - 1);                 /* thread within group */
+	const int slot = warp * C::groups_per_warp + (lane >> (K - 3));
+	u64 *xb = sm_x + (size_t) slot * C::xbuf;
+	const bool fold = INV && s0 == 0;
+	const ulonglong2 fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+	const ulonglong2 fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
+
+	/* tiles of the CTA: (b_local, h), h fastest; group `slot` takes every
+	 * groups_per_cta-th one.  The loop count is uniform across the warp. */
+	const unsigned ntiles = nb << p.hgroup_log2;
+	for (unsigned base = 0; base < ntiles; base += C::groups_per_cta) {
+		const unsigned idx = base + slot;
+		const bool active = idx < ntiles;
+		const unsigned h = idx & (hgroup - 1), bl = idx >> p.hgroup_log2;
+		const u64 poly = (b0 + bl) * p.limbs + limb;
+		const u64 off = (poly << L) + ((u64) (H0 + h) << K);
+		const ulonglong2 *twt = sm_tw + ((size_t) h << K);
+		auto tw = [&](int node) { return twt[node]; };
+
+		u64 x[8];
+		constexpr int first = INV ? G::rounds - 1 : 0;
+		if (active) {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				x[e] = p.src[off + G::index(first, t, e)];
+			}
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				x[e] = 0;
+			}
+		}
+
+#pragma unroll
+		for (int rr = 0; rr < G::rounds; rr++) {
+			const int r = INV ? G::rounds - 1 - rr : rr;
+			if (rr > 0) {
+				/* redistribute: previous round's layout -> this round's */
+				const int prev = INV ? r + 1 : r - 1;
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					xb[xpad(G::index(prev, t, e))] = x[e];
+				}
+				__syncwarp();
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					x[e] = xb[xpad(G::index(r, t, e))];
+				}
+			}
+			if (fold) {
+				tile_round<K, INV, true>(x, r, t, tw, q, twoq, fold_a, fold_b);
+			} else {
+				tile_round<K, INV, false>(x, r, t, tw, q, twoq, fold_a, fold_b);
+			}
+		}
+		__syncwarp();
+
+		constexpr int last = INV ? 0 : G::rounds - 1;
+		const bool canon = INV ? s0 == 0 : true;   /* pass with the final stage */
+		if (active) {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				u64 v = x[e];
+				if (canon) {
+					if (!INV) {
+						v = csub(v, twoq);
+					}
+					v = csub(v, q);
+				}
+				p.dst[off + G::index(last, t, e)] = v;
+			}
+		}
+	}
+}
+
+/* column pass: tile = 2^K rows at stride `cstride` = 2^(L-s0-K); the CTA takes
+ * COLS adjacent columns.  threads = 2^(K-3) row groups x COLS columns. */
+template <int K, int CL>
+struct col_cfg {
+	static constexpr int cols_log2 = CL;
+	static constexpr int cols = 1 << CL;
+	static constexpr int threads = 1 << (K - 3 + CL);
+};
+
+template <bool INV, int K, int CL>
+__global__ void __launch_bounds__(1 << (K - 3 + CL))
+ntt_cols_kernel(const fast_pass p) {
+	using G = tile_geom<K>;
+	using C = col_cfg<K, CL>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;           /* [2^K] */
+	u64 *sm_x = (u64 *) (sm_tw + (1 << K));                /* [2^K][COLS] */
+
+	const unsigned L = p.log2n, s0 = p.s0;
+	const unsigned low_bits = L - s0 - K;                  /* log2 of the row stride */
+	const unsigned cgroups_log2 = low_bits - C::cols_log2;
+
+	/* blockIdx.x -> (poly, H, column group), column group fastest */
+	u64 blk = blockIdx.x;
+	const u64 cg = blk & (((u64) 1 << cgroups_log2) - 1);
+	blk >>= cgroups_log2;
+	const u64 H = blk & (((u64) 1 << s0) - 1);
+	const u64 poly = blk >> s0;
+
+	const limb_desc d = p.descs[poly % p.limbs];
+	const u64 q = d.q, twoq = 2 * d.q;
+	const ulonglong2 *tw_g = d.tw + (INV ? ((u64) 1 << L) : 0);
+
+	for (unsigned node = threadIdx.x; node < (1u << K); node += C::threads) {
+		if (node) {
+			const unsigned u = 31 - __clz(node);
+			const u64 root = ((u64) 1 << s0) + H;
+			sm_tw[node] = tw_g[(root << u) + (node - (1u << u))];
+		}
+	}
+
+	const int c = threadIdx.x & (C::cols - 1);
+	const int t = threadIdx.x >> C::cols_log2;             /* row group */
+	const u64 base = (poly << L) + (H << (L - s0)) + (cg << C::cols_log2) + c;
+	auto tw = [&](int node) { return sm_tw[node]; };
+	const bool fold = INV && s0 == 0;
+	const ulonglong2 fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+	const ulonglong2 fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
+
+	u64 x[8];
+	constexpr int first = INV ? G::rounds - 1 : 0;
+#pragma unroll
+	for (int e = 0; e < 8; e++) {
+		x[e] = p.src[base + ((u64) G::index(first, t, e) << low_bits)];
+	}
+	__syncthreads();   /* twiddles staged */
+
+#pragma unroll
+	for (int rr = 0; rr < G::rounds; rr++) {
+		const int r = INV ? G::rounds - 1 - rr : rr;
+		if (rr > 0) {
+			const int prev = INV ? r + 1 : r - 1;
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				sm_x[(G::index(prev, t, e) << C::cols_log2) + c] = x[e];
+			}
+			__syncthreads();
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				x[e] = sm_x[(G::index(r, t, e) << C::cols_log2) + c];
+			}
+		}
+		if (fold) {
+			tile_round<K, INV, true>(x, r, t, tw, q, twoq, fold_a, fold_b);
+		} else {
+			tile_round<K, INV, false>(x, r, t, tw, q, twoq, fold_a, fold_b);
+		}
+	}
+
+	constexpr int last = INV ? 0 : G::rounds - 1;
+	/* the forward transform always ends in a row pass; the inverse ends here
+	 * when this pass holds stage 0 */
+	const bool canon = INV && s0 == 0;
+#pragma unroll
+	for (int e = 0; e < 8; e++) {
+		u64 v = x[e];
+		if (canon) {
+			v = csub(v, q);
+		}
+		p.dst[base + ((u64) G::index(last, t, e) << low_bits)] = v;
+	}
+}
+
+template <bool INV, int K>
+static void run_rows(struct vkhel_ctx *ctx, fast_pass p) {
+	using C = row_cfg<K>;
+	const u64 batch = p.polys / p.limbs;
+	/* enough tiles per CTA to occupy every warp-group: H values first (they
+	 * are contiguous in memory), then batch entries */
+	unsigned hgroup_log2 = 0;
+	while ((1u << hgroup_log2) < (unsigned) C::groups_per_cta
+			&& hgroup_log2 < p.s0
+			&& ((u64) batch << hgroup_log2) < (u64) C::groups_per_cta) {
+		hgroup_log2++;
+	}
+	/* twiddle staging is shared by the batch entries of a CTA; cap the chunk
+	 * so that large batches still spread over the whole GPU */
+	u64 tiles_total = (p.polys << p.s0);
+	unsigned bchunk = (unsigned) ((C::groups_per_cta >> hgroup_log2)
+			? (C::groups_per_cta >> hgroup_log2) : 1);
+	const u64 target_ctas = (u64) ctx->dev.sm_count * 16;
+	while (bchunk * 2 <= batch && bchunk < 16
+			&& tiles_total / ((u64) (bchunk * 2) << hgroup_log2) >= target_ctas) {
+		bchunk *= 2;
+	}
+	if (bchunk > batch) {
+		bchunk = (unsigned) batch;
+	}
+	p.hgroup_log2 = hgroup_log2;
+	p.bchunk = bchunk;
+	const u64 bchunks = (batch + bchunk - 1) / bchunk;
+	const u64 blocks = bchunks * p.limbs * ((1ull << p.s0) >> hgroup_log2);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
+	const size_t smem = ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
+		+ (size_t) C::groups_per_cta * C::xbuf * sizeof(u64);
+	if (smem > 48 * 1024) {
+		/* per device, and cheap: set it on every such launch */
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
+	ntt_rows_kernel<INV, K><<<(unsigned) blocks, FAST_THREADS, smem,
+		ctx_stream(ctx)>>>(p);
+	CUDA_CHECK(cudaGetLastError());
+	ctx->dev.launches++;
+}
+
+template <bool INV, int K, int CL>
+static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
+	using C = col_cfg<K, CL>;
+	const unsigned low_bits = p.log2n - p.s0 - K;
+	VK_REQUIRE(low_bits >= (unsigned) CL,
+			"internal: column pass narrower than its CTA");
+	const u64 blocks = (p.polys << p.s0) << (low_bits - CL);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
+	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
+	ntt_cols_kernel<INV, K, CL><<<(unsigned) blocks, C::threads, smem,
+		ctx_stream(ctx)>>>(p);
+	CUDA_CHECK(cudaGetLastError());
+	ctx->dev.launches++;
+}
+
+/* 256 threads per CTA, i.e. 2^(11-K) columns; the 8-point column pass of
+ * n = 2^9 and 2^10 has only 64 / 128 columns to offer */
+template <bool INV, int K>
+static void run_cols(struct vkhel_ctx *ctx, const fast_pass &p) {
+	const unsigned low_bits = p.log2n - p.s0 - K;
+	if (K == 3 && low_bits == 6) {
+		run_cols_cl<INV, 3, 6>(ctx, p);
+	} else if (K == 3 && low_bits == 7) {
+		run_cols_cl<INV, 3, 7>(ctx, p);
+	} else {
+		run_cols_cl<INV, K, 11 - K>(ctx, p);
+	}
+}
+
+template <bool INV>
+static void run_rows_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
+	switch (k) {
+	case 3: run_rows<INV, 3>(ctx, p); break;
+	case 4: run_rows<INV, 4>(ctx, p); break;
+	case 5: run_rows<INV, 5>(ctx, p); break;
+	case 6: run_rows<INV, 6>(ctx, p); break;
+	case 7: run_rows<INV, 7>(ctx, p); break;
+	case 8: run_rows<INV, 8>(ctx, p); break;
+	default: VK_DIE("internal: row pass of %u stages", k);
+	}
+}
+
+template <bool INV>
+static void run_cols_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
+	switch (k) {
+	case 3: run_cols<INV, 3>(ctx, p); break;
+	case 4: run_cols<INV, 4>(ctx, p); break;
+	case 5: run_cols<INV, 5>(ctx, p); break;
+	case 6: run_cols<INV, 6>(ctx, p); break;
+	case 7: run_cols<INV, 7>(ctx, p); break;
+	case 8: run_cols<INV, 8>(ctx, p); break;
+	default: VK_DIE("internal: column pass of %u stages", k);
+	}
+}
+
+/* stage split of the fast path: [lead (generic, strided)] [col] [row] */
+struct fast_plan {
+	unsigned lead, kcol, krow;
+};
+
+static fast_plan plan_fast(unsigned log2n) {
+	fast_plan pl = { 0, 0, 0 };
+	if (log2n <= 8) {
+		pl.krow = log2n;
+	} else if (log2n <= 16) {
+		pl.krow = log2n - 8 >= 3 ? 8 : log2n - 3;
+		pl.kcol = log2n - pl.krow;
+	} else {
+		pl.krow = 8;
+		pl.kcol = 8;
+		pl.lead = log2n - 16;
+	}
+	return pl;
+}
+
+template <bool INV>
+static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
+		const limb_desc *descs, uint64_t limbs, uint64_t polys,
+		unsigned log2n) {
+	const fast_plan pl = plan_fast(log2n);
+	fast_pass p;
+	p.descs = descs;
+	p.limbs = (unsigned) limbs;
+	p.log2n = log2n;
+	p.polys = polys;
+	p.hgroup_log2 = 0;
+	p.bchunk = 1;
+
+	gen_pass lead;
+	lead.descs = descs;
+	lead.limbs = (unsigned) limbs;
+	lead.log2n = log2n;
+	lead.s0 = 0;
+	lead.k = pl.lead;
+	lead.tiles = polys;
+	lead.last = false;
+
+	if (!INV) {
+		const u64 *cur = src;
+		if (pl.lead) {
+			lead.src = cur;
+			lead.dst = dst;
+			run_generic_pass<false, false>(ctx, lead);
+			cur = dst;
+		}
+		if (pl.kcol) {
+			p.src = cur;
+			p.dst = dst;
+			p.s0 = pl.lead;
+			run_cols_k<false>(ctx, p, pl.kcol);
+			cur = dst;
+		}
+		p.src = cur;
+		p.dst = dst;
+		p.s0 = pl.lead + pl.kcol;
+		run_rows_k<false>(ctx, p, pl.krow);
+	} else {
+		p.src = src;
+		p.dst = dst;
+		p.s0 = pl.lead + pl.kcol;
+		run_rows_k<true>(ctx, p, pl.krow);
+		if (pl.kcol) {
+			p.src = dst;
+			p.s0 = pl.lead;
+			run_cols_k<true>(ctx, p, pl.kcol);
+		}
+		if (pl.lead) {
+			lead.src = dst;
+			lead.dst = dst;
+			lead.last = true;
+			run_generic_pass<true, false>(ctx, lead);
+		}
+	}
+}
+
+/* ======================================================================================
  * Dispatch
  * ====================================================================================== */
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
@@ -239,6 +673,11 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 			log2n);
 	VK_REQUIRE(q_max < (1ull << 63), "NTT modulus must be below 2^63");
 	const bool strict = q_max >= (1ull << 62);
+	if (!strict && log2n >= 3 && !getenv("VKHEL_FORCE_GENERIC")) {
+		if (inverse) run_fast<true>(ctx, src, dst, descs, limbs, polys, log2n);
+		else run_fast<false>(ctx, src, dst, descs, limbs, polys, log2n);
+		return;
+	}
 	if (inverse) {
 		if (strict) run_generic<true, true>(ctx, src, dst, descs, limbs, polys, log2n);
 		else run_generic<true, false>(ctx, src, dst, descs, limbs, polys, log2n);
