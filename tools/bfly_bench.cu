@@ -1,0 +1,215 @@
+/*
+ * Butterfly formulation micro-benchmark: which way of writing the lazy
+ * Cooley-Tukey / Gentleman-Sande butterfly costs the fewest FMA-pipe issue
+ * slots on sm_100a.  Each thread keeps 4 (x,y) pairs in registers (the ILP of
+ * one radix-8 stage) and applies the butterfly ITERS times; 1024 threads per
+ * SM on every SM.  Output: butterflies per clock per SM (clock64 based).
+ *
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/bin/bfly_bench tools/bfly_bench.cu
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+#define PAIRS 4
+#define ITERS 2048
+
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
+	fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+struct consts { u64 q, twoq, w, wp; };
+
+template <class B>
+__global__ void __launch_bounds__(1024) bench(u64 *sink, u64 *cycles, consts c, B b) {
+	u64 x[PAIRS], y[PAIRS];
+#pragma unroll
+	for (int i = 0; i < PAIRS; i++) {
+		x[i] = (c.q >> 1) + threadIdx.x * 977 + i;
+		y[i] = (c.q >> 2) + threadIdx.x * 131 + 7 * i;
+	}
+	__syncthreads();
+	const u64 t0 = clock64();
+#pragma unroll 1
+	for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+		for (int i = 0; i < PAIRS; i++) {
+			b(x[i], y[i], c);
+		}
+		/* rotate the pairs so that x and y roles mix as in a real transform */
+		const u64 tmp = y[0];
+#pragma unroll
+		for (int i = 0; i < PAIRS - 1; i++) y[i] = y[i + 1];
+		y[PAIRS - 1] = tmp;
+	}
+	const u64 t1 = clock64();
+	u64 acc = 0;
+#pragma unroll
+	for (int i = 0; i < PAIRS; i++) acc ^= x[i] ^ y[i];
+	if (acc == 0x1234567) sink[0] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+__device__ __forceinline__ u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
+
+/* ---- V0: Harvey CT as shipped (modarith.cuh ct_lazy) ---- */
+struct ct_v0 { static const char *name() { return "CT v0 harvey (csub x, exact mulhi)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub(x, c.twoq);
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
+/* ---- V1: no range correction (cost of the csub) ---- */
+struct ct_v1 { static const char *name() { return "CT v1 no csub (range grows 2q/stage)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		const u64 xo = x;
+		x = xo + t; y = xo - t + c.twoq;
+	} };
+
+/* approximate high product: drops the low x low partial product and the
+ * carries of the middle column: result in [hi-2, hi] */
+__device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {
+	const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+	return (u64) a1 * b1 + __umulhi(a1, b0) + __umulhi(a0, b1);
+}
+
+/* ---- V2: approximate mulhi, t in [0,4q), no csub ---- */
+struct ct_v2 { static const char *name() { return "CT v2 approx mulhi (3 hi products), no csub"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 t = y * c.w - mulhi_approx(y, c.wp) * c.q;
+		const u64 xo = x;
+		x = xo + t; y = xo - t + 2 * c.twoq;
+	} };
+
+/* ---- V3: approximate mulhi + csub ---- */
+struct ct_v3 { static const char *name() { return "CT v3 approx mulhi + csub(x,4q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub(x, 2 * c.twoq);
+		const u64 t = y * c.w - mulhi_approx(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + 2 * c.twoq;
+	} };
+
+/* ---- V4: csub written with the sign of the difference ---- */
+struct ct_v4 { static const char *name() { return "CT v4 harvey, csub via sign mask"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 d = x - c.twoq;
+		const u64 xr = ((long long) d < 0) ? x : d;   /* valid while x < 2^63 */
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
+/* ---- V5: fold the correction into 3-input adds (keeps adds on the ALU pipe) ---- */
+struct ct_v5 { static const char *name() { return "CT v5 harvey, correction folded into 3-input adds"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 corr = x >= c.twoq ? c.twoq : 0;     /* 0 or 2q */
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		const u64 xo = x;
+		x = xo - corr + t;
+		y = xo + (c.twoq - corr) - t;
+	} };
+
+/* ---- V6: min-based csub: min(x, x - 2q) as unsigned ---- */
+struct ct_v6 { static const char *name() { return "CT v6 harvey, csub = umin(x, x-2q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = min(x, x - c.twoq);
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
+/* ---- mulhi through explicit 32-bit partial products, carries kept minimal ---- */
+__device__ __forceinline__ u64 mulhi_explicit(u64 a, u64 b) {
+	const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+	const u64 p00 = (u64) a0 * b0;
+	const u64 p01 = (u64) a0 * b1 + (p00 >> 32);        /* cannot overflow */
+	const u64 p10 = (u64) a1 * b0 + (u32) p01;          /* cannot overflow */
+	return (u64) a1 * b1 + (p01 >> 32) + (p10 >> 32);
+}
+struct ct_v7 { static const char *name() { return "CT v7 harvey, mulhi as 4 mad.wide chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub(x, c.twoq);
+		const u64 t = y * c.w - mulhi_explicit(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
+/* ---- GS variants ---- */
+struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = csub(s, c.twoq);
+		y = d * c.w - __umul64hi(d, c.wp) * c.q;
+	} };
+struct gs_v1 { static const char *name() { return "GS v1 no csub"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = s;
+		y = d * c.w - __umul64hi(d, c.wp) * c.q;
+	} };
+struct gs_v2 { static const char *name() { return "GS v2 approx mulhi, no csub"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = s;
+		y = d * c.w - mulhi_approx(d, c.wp) * c.q;
+	} };
+struct gs_v6 { static const char *name() { return "GS v6 csub = umin"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = min(s, s - c.twoq);
+		y = d * c.w - __umul64hi(d, c.wp) * c.q;
+	} };
+
+/* ---- pieces ---- */
+struct only_shoup { static const char *name() { return "shoup_lazy only (1 per pair)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		y = y * c.w - __umul64hi(y, c.wp) * c.q; x ^= y;
+	} };
+struct only_shoup_approx { static const char *name() { return "shoup approx only (1 per pair)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		y = y * c.w - mulhi_approx(y, c.wp) * c.q; x ^= y;
+	} };
+struct only_mulhi32 { static const char *name() { return "2x mul.hi.u32 only"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u32 r = __umulhi((u32) y, (u32) c.wp) + __umulhi((u32) (y >> 32), (u32) (c.wp >> 32));
+		y = ((u64) r << 32) | (u32) x; x += y;
+	} };
+
+template <class B>
+static void run(int sms, const consts &c) {
+	u64 *sink, *cycles;
+	CHECK(cudaMalloc(&sink, 8));
+	CHECK(cudaMalloc(&cycles, sms * sizeof(u64)));
+	for (int rep = 0; rep < 2; rep++) {
+		bench<<<sms, 1024>>>(sink, cycles, c, B());
+		CHECK(cudaDeviceSynchronize());
+	}
+	std::vector<u64> h(sms);
+	CHECK(cudaMemcpy(h.data(), cycles, sms * sizeof(u64), cudaMemcpyDeviceToHost));
+	double cyc = 0;
+	for (int i = 0; i < sms; i++) cyc += (double) h[i];
+	cyc /= sms;
+	const double per_sm = 1024.0 * PAIRS * ITERS;
+	printf("%-52s %6.3f bfly/clk/SM  -> %7.1f Gbfly/s @1.965GHz x148\n", B::name(),
+			per_sm / cyc, per_sm / cyc * 148 * 1.965);
+	CHECK(cudaFree(sink));
+	CHECK(cudaFree(cycles));
+}
+
+int main() {
+	cudaDeviceProp prop;
+	CHECK(cudaGetDeviceProperties(&prop, 0));
+	const int sms = prop.multiProcessorCount;
+	consts c;
+	c.q = 1152921504606584833ull; c.twoq = 2 * c.q;
+	c.w = 987813353222176621ull;
+	c.wp = (u64) ((((unsigned __int128) c.w) << 64) / c.q);
+	run<ct_v0>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
+	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
+	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);
+	return 0;
+}
