@@ -22,6 +22,7 @@ typedef unsigned int u32;
 	fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 struct consts { u64 q, twoq, w, wp; };
+__shared__ ulonglong2 sm_tw[256];
 
 template <class B>
 __global__ void __launch_bounds__(1024) bench(u64 *sink, u64 *cycles, consts c, B b) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(1024) bench(u64 *sink, u64 *cycles, consts c, 
 		x[i] = (c.q >> 1) + threadIdx.x * 977 + i;
 		y[i] = (c.q >> 2) + threadIdx.x * 131 + 7 * i;
 	}
+	if (threadIdx.x < 256) sm_tw[threadIdx.x] = make_ulonglong2(c.w + threadIdx.x, c.wp - threadIdx.x);
 	__syncthreads();
 	const u64 t0 = clock64();
 #pragma unroll 1
@@ -137,6 +139,26 @@ struct ct_v7 { static const char *name() { return "CT v7 harvey, mulhi as 4 mad.
 		x = xr + t; y = xr - t + c.twoq;
 	} };
 
+/* ---- V8: as v0 but w, w' are per-thread values in ordinary registers ---- */
+struct ct_v8 { static const char *name() { return "CT v8 harvey, per-thread w/w' (vector regs)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		/* derive thread-dependent twiddles once; the compiler cannot keep
+		 * them in uniform registers */
+		const u64 w = c.w ^ (threadIdx.x & 1), wp = c.wp ^ (threadIdx.x & 2);
+		const u64 xr = csub(x, c.twoq);
+		const u64 t = y * w - __umul64hi(y, wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
+/* ---- V9: twiddle pair fetched from shared memory for every butterfly ---- */
+struct ct_v9 { static const char *name() { return "CT v9 harvey, w/w' LDS.128 per butterfly"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const ulonglong2 w = sm_tw[(threadIdx.x + (unsigned) x) & 255];
+		const u64 xr = csub(x, c.twoq);
+		const u64 t = y * w.x - __umul64hi(y, w.y) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -178,13 +200,15 @@ struct only_mulhi32 { static const char *name() { return "2x mul.hi.u32 only"; }
 		y = ((u64) r << 32) | (u32) x; x += y;
 	} };
 
+static int g_threads = 1024;
+
 template <class B>
 static void run(int sms, const consts &c) {
 	u64 *sink, *cycles;
 	CHECK(cudaMalloc(&sink, 8));
 	CHECK(cudaMalloc(&cycles, sms * sizeof(u64)));
 	for (int rep = 0; rep < 2; rep++) {
-		bench<<<sms, 1024>>>(sink, cycles, c, B());
+		bench<<<sms, g_threads>>>(sink, cycles, c, B());
 		CHECK(cudaDeviceSynchronize());
 	}
 	std::vector<u64> h(sms);
@@ -192,7 +216,7 @@ static void run(int sms, const consts &c) {
 	double cyc = 0;
 	for (int i = 0; i < sms; i++) cyc += (double) h[i];
 	cyc /= sms;
-	const double per_sm = 1024.0 * PAIRS * ITERS;
+	const double per_sm = (double) g_threads * PAIRS * ITERS;
 	printf("%-52s %6.3f bfly/clk/SM  -> %7.1f Gbfly/s @1.965GHz x148\n", B::name(),
 			per_sm / cyc, per_sm / cyc * 148 * 1.965);
 	CHECK(cudaFree(sink));
@@ -207,7 +231,14 @@ int main() {
 	c.q = 1152921504606584833ull; c.twoq = 2 * c.q;
 	c.w = 987813353222176621ull;
 	c.wp = (u64) ((((unsigned __int128) c.w) << 64) / c.q);
-	run<ct_v0>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	/* occupancy sweep: how many warps per SM does the butterfly need */
+	for (int th = 128; th <= 1024; th += 128) {
+		g_threads = th;
+		printf("[%4d threads/SM] ", th);
+		run<ct_v0>(sms, c);
+	}
+	g_threads = 1024;
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);

@@ -10,7 +10,9 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "lib", "libvkhel.so")
+# $VKHEL_LIB_PATH lets kernel experiments load an alternative build
+LIB_PATH = os.environ.get("VKHEL_LIB_PATH",
+                          os.path.join(_PKG, "lib", "libvkhel.so"))
 
 _u64 = ctypes.c_uint64
 _p64 = ctypes.POINTER(ctypes.c_uint64)

@@ -40,24 +40,53 @@ struct tile_geom {
 	__host__ __device__ static constexpr bool full(int r) {
 		return cnt(r) == 3;
 	}
-	/* tile index of register e of group-thread t in round r */
-	__device__ __forceinline__ static int index(int r, int t, int e) {
+	/* The tile index of register e of group-thread t in round r is
+	 * tbase(r,t) + eoff(r,e): the two parts occupy disjoint bits, so every
+	 * address derived from it is "per-thread base + compile-time constant"
+	 * and the loads/stores carry immediate offsets. */
+	__device__ __forceinline__ static int tbase(int r, int t) {
 		if (full(r)) {
 			const int p = K - 3 * (r + 1);
-			return ((t >> p) << (p + 3)) | (e << p) | (t & ((1 << p) - 1));
+			return ((t >> p) << (p + 3)) | (t & ((1 << p) - 1));
+		}
+		return t << last_cnt;
+	}
+	__host__ __device__ static constexpr int eoff(int r, int e) {
+		if (full(r)) {
+			return e << (K - 3 * (r + 1));
+		}
+		return ((e >> last_cnt) << (K - 3 + last_cnt))
+			| (e & ((1 << last_cnt) - 1));
+	}
+	__device__ __forceinline__ static int index(int r, int t, int e) {
+		return tbase(r, t) + eoff(r, e);
+	}
+
+	/* Twiddle group g = i >> (K-u) of stage j of round r, same split:
+	 * gbase(r,j,t) + goff(r,j,e) (e: the butterfly's upper register) */
+	__device__ __forceinline__ static int gbase(int r, int j, int t) {
+		if (full(r)) {
+			return (t >> (K - 3 * (r + 1))) << j;
+		}
+		return t << j;
+	}
+	__host__ __device__ static constexpr int goff(int r, int j, int e) {
+		if (full(r)) {
+			return e >> (3 - j);
 		}
 		const int c = last_cnt;
-		return ((e >> c) << (K - 3 + c)) | (t << c) | (e & ((1 << c) - 1));
+		return ((e >> c) << (K - 3 + j)) | ((e & ((1 << c) - 1)) >> (c - j));
 	}
 };
 
 /* One round of butterflies on x[0..7].
- *   TW(node) returns the (w, w') pair of local twiddle node `node`.
+ *   twt: the tile's twiddle subtree in shared memory, twt[node] = (w, w')
  *   FOLD: inverse only -- local stage 0 is global stage 0: multiply by n^-1
  *         (fold_a = n^-1, fold_b = inv_root[1] * n^-1) instead of node 1. */
-template <int K, bool INV, bool FOLD, class TW>
+template <int K, bool INV, bool FOLD>
 __device__ __forceinline__ void tile_round(u64 (&x)[8], int r, int t,
-		const TW &tw, u64 q, u64 twoq, ulonglong2 fold_a, ulonglong2 fold_b) {
+		const ulonglong2 *twt, u64 q, u64 twoq, ulonglong2 fold_a,
+		ulonglong2 fold_b) {
 	using G = tile_geom<K>;
 	const int cnt = G::cnt(r);
 #pragma unroll
@@ -68,31 +97,11 @@ __device__ __forceinline__ void tile_round(u64 (&x)[8], int r, int t,
 		const int j = INV ? cnt - 1 - step : step;  /* stage within the round */
 		const int u = 3 * r + j;                    /* local stage */
 		const int beta = cnt - 1 - j;               /* pair bit inside e */
-		/* group number g = i >> (K-u) splits into a thread part and the
-		 * bits of e above the pair bit */
-		int g_thread;
-		if (G::full(r)) {
-			const int p = K - 3 * (r + 1);
-			g_thread = (t >> p) << j;
-		} else {
-			g_thread = t << j;
-		}
+		const ulonglong2 *twp = twt + (1 << u) + G::gbase(r, j, t);
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
 			if (e & (1 << beta)) {
 				continue;
-			}
-			int g;
-			if (G::full(r)) {
-				g = g_thread | (e >> (beta + 1));
-			} else {
-				/* passengers (top bits) then thread bits then e's upper
-				 * pair bits */
-				const int c = cnt;
-				const int e_hi = e >> c;
-				const int e_lo = e & ((1 << c) - 1);
-				g = (e_hi << (K - 3 + c - (c - j))) | g_thread
-					| (e_lo >> (beta + 1));
 			}
 			u64 &X = x[e];
 			u64 &Y = x[e | (1 << beta)];
@@ -102,7 +111,7 @@ __device__ __forceinline__ void tile_round(u64 (&x)[8], int r, int t,
 				X = shoup_lazy(s, fold_a.x, fold_a.y, q);
 				Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
 			} else {
-				const ulonglong2 w = tw((1 << u) + g);
+				const ulonglong2 w = twp[G::goff(r, j, e)];
 				if (INV) {
 					gs_lazy(X, Y, w.x, w.y, q, twoq);
 				} else {
