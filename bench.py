@@ -36,14 +36,34 @@ LOG2N = 16
 N = 1 << LOG2N
 LIMBS = 32
 BATCH = 16
+E2E_CHUNKS = 4
 POLYS = LIMBS * BATCH
 METRIC = "64-bit NTTs/sec at n=2^16"
 # measured per-GPU integer peaks (profiles/r01_bfly_bench.txt)
 BFLY_PEAK_G = 828.0          # lazy Harvey butterflies/s, as compiled by ptxas
 BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
+# DRAM bytes of one step (4 launches) from the ncu --set full capture
+# profiles/r01_ntt_v3_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
+NCU_TRAFFIC_BYTES_PER_STEP = int((268.594 + 229.818 + 301.891 + 216.038
+                                  + 301.996 + 217.487 + 268.612 + 217.899) * 1e6)
 WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
             "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
             "step = forward + inverse of the whole batch")
+
+
+class c_stdout_to_stderr:
+    """The library prints `using physical device N: ...` on stdout like the
+    reference (src/vulkan.c:171); keep this program's stdout to the one JSON
+    line by pointing fd 1 at stderr while a context is created."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 # ---- clocks --------------------------------------------------------------------------
@@ -234,7 +254,8 @@ def run_native_arm(args):
 
     primes = params.ntt_primes(LIMBS)
     psis = [params.find_psi(N, q) for q in primes]
-    ctx = vk.Context(local_rank)
+    with c_stdout_to_stderr():
+        ctx = vk.Context(local_rank)
     tables = [vk.NttTables(N, q, w) for q, w in zip(primes, psis)]
 
     host_in = vk.host_alloc(POLYS * N)
@@ -249,11 +270,25 @@ def run_native_arm(args):
         ctx.forward_transform_rns(data, work, tables, BATCH)
         ctx.inverse_transform_rns(work, work, tables, BATCH)
 
+    # end-to-end path: the batch moves in E2E_CHUNKS slices of whole batch
+    # entries, each slice on its own device vector, two sets of slices used
+    # alternately: upload (H2D copy stream), both transforms (compute stream)
+    # and download (D2H copy stream) of different slices overlap.
+    chunk_batch = BATCH // E2E_CHUNKS
+    chunk_elems = chunk_batch * LIMBS * N
+    slices = [[ctx.vector(chunk_elems, zero=False) for _ in range(E2E_CHUNKS)]
+              for _ in range(2)]
+    e2e_state = {"step": 0}
+
     def step_e2e():
-        data.upload(host_in)
-        ctx.forward_transform_rns(data, work, tables, BATCH)
-        ctx.inverse_transform_rns(work, work, tables, BATCH)
-        work.download(host_out)
+        cur = slices[e2e_state["step"] & 1]
+        e2e_state["step"] += 1
+        for c, v in enumerate(cur):
+            v.upload(host_in, count=chunk_elems, host_offset=c * chunk_elems)
+            ctx.forward_transform_rns(v, v, tables, chunk_batch)
+            ctx.inverse_transform_rns(v, v, tables, chunk_batch)
+            v.download(host_out, count=chunk_elems,
+                       host_offset=c * chunk_elems)
 
     timer = ctx.timer()
 
@@ -293,8 +328,9 @@ def run_native_arm(args):
     ms_fwd, _ = timed(fwd_only, args.steps, 1)
     ms_inv, _ = timed(inv_only, args.steps, 1)
 
-    ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 10)), 1)
+    host_out.array[:] = 0
     e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
     ok = ok and bool(np.array_equal(host_out.array, host_in.array))
 
     ntts_per_step = 2 * POLYS
@@ -323,14 +359,20 @@ def run_native_arm(args):
                     "h2d_bytes_per_step": POLYS * N * 8,
                     "d2h_bytes_per_step": POLYS * N * 8,
                     "steps": e2e_steps,
-                    "path": "vkhel_vector_upload (pinned) -> "
-                            "forward_transform_rns -> inverse_transform_rns "
-                            "-> vkhel_vector_download, one stream"},
+                    "path": "per 64 MiB slice: vkhel_vector_upload (pinned) "
+                            "-> forward_transform_rns -> "
+                            "inverse_transform_rns -> vkhel_vector_download;"
+                            " copies on the context's H2D/D2H streams "
+                            "overlap with each other and with compute"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_BYTES_PER_STEP,
+                "traffic_source": "ncu --set full, profiles/"
+                                  "r01_ntt_v3_ncu_full.txt (two passes per "
+                                  "transform: ~2x the algorithmic bytes)",
                 "peak_source": peak_src,
                 "kernel": "whole step (forward + inverse NTT, all passes)",
                 "algorithmic_bytes_per_step": algo_bytes,
@@ -360,7 +402,7 @@ def run_native_arm(args):
         print(json.dumps(line))
 
     timer.destroy()
-    for v in (data, work):
+    for v in [data, work] + slices[0] + slices[1]:
         v.destroy()
     for t in tables:
         t.destroy()

@@ -26,7 +26,10 @@ struct device_ctx {
 	int sm_count;
 	size_t smem_optin;   /* max dynamic shared memory per block */
 	size_t l2_bytes;
-	void *stream;        /* cudaStream_t */
+	void *stream;        /* cudaStream_t: every kernel and the map()/copy path */
+	void *stream_h2d;    /* vkhel_vector_upload: host -> device copy engine */
+	void *stream_d2h;    /* vkhel_vector_download: device -> host copy engine */
+	void *ev_scratch;    /* cudaEvent_t used to fork from the compute stream */
 	void *mem_pool;      /* cudaMemPool_t: stream-ordered allocator */
 	struct pinned_slot pinned[VKHEL_PINNED_SLOTS]; /* map() staging cache */
 	void *flush_buf;     /* L2 flush scratch, allocated on demand */

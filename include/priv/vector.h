@@ -27,6 +27,13 @@ struct vkhel_vector {
 	size_t length;
 	struct backing_memory device;
 	struct backing_memory host; /* non-NULL ptr while mapped */
+
+	/* asynchronous transfer tracking (vkhel_vector_upload/_download run on
+	 * the context's copy streams): completion event of the last transfer
+	 * that touched this vector, and whether the compute stream has yet to
+	 * wait for it */
+	void *xfer_event;   /* cudaEvent_t, created on first use */
+	int xfer_pending;
 };
 
 void vkhel_vector_dbgprint(const struct vkhel_vector *);

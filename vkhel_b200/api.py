@@ -195,13 +195,17 @@ class Vector:
         lib().vkhel_vector_unmap(self.handle)
         return out
 
-    def upload(self, pinned, offset=0, count=None):
-        count = pinned.count if count is None else count
-        lib().vkhel_vector_upload(self.handle, pinned.ptr, offset, count)
+    def upload(self, pinned, offset=0, count=None, host_offset=0):
+        """enqueue host -> device: pinned[host_offset:+count] -> self[offset:]"""
+        count = pinned.count - host_offset if count is None else count
+        lib().vkhel_vector_upload(self.handle, pinned.ptr + 8 * host_offset,
+                                  offset, count)
 
-    def download(self, pinned, offset=0, count=None):
-        count = pinned.count if count is None else count
-        lib().vkhel_vector_download(self.handle, pinned.ptr, offset, count)
+    def download(self, pinned, offset=0, count=None, host_offset=0):
+        """enqueue device -> host: self[offset:+count] -> pinned[host_offset:]"""
+        count = pinned.count - host_offset if count is None else count
+        lib().vkhel_vector_download(self.handle, pinned.ptr + 8 * host_offset,
+                                    offset, count)
 
 
 class Context:

@@ -85,6 +85,14 @@ extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
 	cudaStream_t stream;
 	CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 	dev->stream = stream;
+	cudaStream_t copy_stream;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+	dev->stream_h2d = copy_stream;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+	dev->stream_d2h = copy_stream;
+	cudaEvent_t fork_event;
+	CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+	dev->ev_scratch = fork_event;
 
 	cudaMemPoolProps props;
 	memset(&props, 0, sizeof(props));
@@ -105,7 +113,12 @@ extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
 extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	enter_device(dev->device);
 	cudaStream_t stream = (cudaStream_t) dev->stream;
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_h2d));
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_d2h));
 	CUDA_CHECK(cudaStreamSynchronize(stream));
+	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_h2d));
+	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_d2h));
+	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_scratch));
 
 	plan_cache *cache = (plan_cache *) dev->plan_cache;
 	for (rns_plan &plan : cache->plans) {
@@ -160,6 +173,8 @@ extern "C" int vkhel_ctx_device(const struct vkhel_ctx *ctx) {
 extern "C" void vkhel_ctx_sync(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
 	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) ctx->dev.stream_h2d));
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) ctx->dev.stream_d2h));
 }
 
 extern "C" void *vkhel_ctx_stream(struct vkhel_ctx *ctx) {
@@ -413,6 +428,14 @@ extern "C" void vkhel_timer_start(struct vkhel_timer *timer) {
 
 extern "C" void vkhel_timer_stop(struct vkhel_timer *timer) {
 	ctx_enter(timer->ctx);
+	/* join the copy streams first, so that the interval covers uploads and
+	 * downloads enqueued since start as well as the kernels */
+	struct device_ctx *dev = &timer->ctx->dev;
+	cudaEvent_t join = (cudaEvent_t) dev->ev_scratch;
+	CUDA_CHECK(cudaEventRecord(join, (cudaStream_t) dev->stream_h2d));
+	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(timer->ctx), join, 0));
+	CUDA_CHECK(cudaEventRecord(join, (cudaStream_t) dev->stream_d2h));
+	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(timer->ctx), join, 0));
 	CUDA_CHECK(cudaEventRecord(timer->stop, ctx_stream(timer->ctx)));
 }
 

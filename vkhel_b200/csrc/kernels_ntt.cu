@@ -249,20 +249,26 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
  * passes stay lazy ([0,4q) forward, [0,2q) inverse) in the result vector.
  * ====================================================================================== */
 #define FAST_THREADS 256
-#ifndef FAST_PREFETCH
-#define FAST_PREFETCH 0   /* 1: load the next tile before computing this one */
+/* tuning knobs (tools/build_variant.sh): tiles per thread and occupancy targets */
+/* NP = 2 (two tiles per thread sharing each twiddle fetch) measured within 2 %
+ * of NP = 1 on B200 (lower occupancy cancels the saved LDS): default 1 */
+#ifndef ROWS_NP
+#define ROWS_NP 1
 #endif
-#ifndef FAST_PERSISTENT
-#define FAST_PERSISTENT 0 /* 1: grid = resident CTAs, each walks a unit range */
+#ifndef COLS_NP
+#define COLS_NP 1
 #endif
-#ifndef FAST_UNITS_PER_CTA
-#define FAST_UNITS_PER_CTA 1
+#ifndef ROWS_MIN_CTAS_NP1
+#define ROWS_MIN_CTAS_NP1 5
 #endif
-#ifndef ROWS_MIN_CTAS
-#define ROWS_MIN_CTAS 4
+#ifndef ROWS_MIN_CTAS_NP2
+#define ROWS_MIN_CTAS_NP2 3
 #endif
-#ifndef COLS_MIN_THREADS
-#define COLS_MIN_THREADS 1024
+#ifndef COLS_MIN_THREADS_NP1
+#define COLS_MIN_THREADS_NP1 1280
+#endif
+#ifndef COLS_MIN_THREADS_NP2
+#define COLS_MIN_THREADS_NP2 768
 #endif
 
 struct fast_pass {
@@ -273,57 +279,47 @@ struct fast_pass {
 	unsigned log2n;
 	unsigned s0;          /* first stage of the pass */
 	u64 polys;            /* batch * limbs */
-	u64 units;            /* work units of the pass (see each kernel) */
-	unsigned hgroup_log2; /* row pass: consecutive H per unit */
-	unsigned bchunk;      /* row pass: batch entries per unit */
+	unsigned hgroup_log2; /* row pass: consecutive H per CTA */
+	unsigned bchunk;      /* row pass: batch entries per CTA */
 };
 
-/* Ampere-style asynchronous copy (LDGSTS): twiddles of the next work unit
- * stream into shared memory while the current unit is being computed */
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-	const unsigned saddr = (unsigned) __cvta_generic_to_shared(smem);
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-			:: "r"(saddr), "l"(gmem) : "memory");
-}
-
-__device__ __forceinline__ void cp_async_commit() {
-	asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__device__ __forceinline__ void cp_async_wait_all() {
-	asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-/* contiguous, balanced share of `units` for CTA `cta` of `ctas` */
-__device__ __forceinline__ void cta_share(u64 units, unsigned ctas,
-		unsigned cta, u64 &begin, u64 &end) {
-	const u64 base = units / ctas, extra = units % ctas;
-	begin = cta * base + (cta < extra ? cta : extra);
-	end = begin + base + (cta < extra ? 1 : 0);
-}
-
 /* padded position of tile element i in a warp-group's exchange buffer: 4 words
- * of padding per 32 keep the strided reads of the second round conflict-free */
+ * of padding per 32 keep the strided reads of the second round conflict-free.
+ * Additive over disjoint bit fields, like the tile index itself. */
 __host__ __device__ constexpr int xpad(int i) {
 	return i + ((i >> 5) << 2);
+}
+
+/* stage the twiddle subtrees rooted at nodes 2^s0 + H0 .. + hgroup - 1 */
+template <int K>
+__device__ __forceinline__ void stage_twiddles(ulonglong2 *sm_tw,
+		const ulonglong2 *tw_g, unsigned s0, u64 H0, unsigned hgroup,
+		unsigned threads) {
+	for (unsigned v = threadIdx.x; v < (hgroup << K); v += threads) {
+		const unsigned h = v >> K, node = v & ((1u << K) - 1);
+		if (node) {
+			const unsigned u = 31 - __clz(node);
+			const u64 root = ((u64) 1 << s0) + H0 + h;
+			sm_tw[v] = tw_g[(root << u) + (node - (1u << u))];
+		}
+	}
 }
 
 template <int K>
 struct row_cfg {
 	static constexpr int tile = 1 << K;
-	static constexpr int xbuf = tile + ((tile >> 5) << 2) + 4; /* words per group */
+	static constexpr int xbuf = tile + ((tile >> 5) << 2) + 4; /* words per tile */
 	static constexpr int group = 1 << (K - 3);                 /* lanes per tile */
 	static constexpr int groups_per_warp = 32 / group;
 	static constexpr int groups_per_cta = (FAST_THREADS / 32) * groups_per_warp;
 };
 
-/* Row pass.  Work unit = (batch chunk, limb, H group): `bchunk` batch entries
- * of 2^hgroup_log2 consecutive tiles that share one staged twiddle set.  The
- * grid is persistent (a few CTAs per SM); a CTA walks a contiguous range of
- * units, prefetching the next tile into registers and the next unit's twiddles
- * into the other half of a double buffer. */
-template <bool INV, int K>
-__global__ void __launch_bounds__(FAST_THREADS, ROWS_MIN_CTAS)
+/* Row pass.  CTA = (batch chunk, limb, H group): `bchunk` batch entries of
+ * 2^hgroup_log2 consecutive tiles sharing one staged twiddle set.  A warp-group
+ * of 2^(K-3) lanes carries NP batch entries of one tile position at a time. */
+template <bool INV, int K, int NP>
+__global__ void __launch_bounds__(FAST_THREADS,
+		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const fast_pass p) {
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
@@ -331,399 +327,259 @@ ntt_rows_kernel(const fast_pass p) {
 
 	const unsigned L = p.log2n, s0 = p.s0;       /* s0 + K == L */
 	const unsigned hgroup = 1u << p.hgroup_log2;
-	const unsigned tw_words = hgroup << K;                       /* pairs per buffer */
-	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;                 /* [2][hgroup][2^K] */
-	u64 *sm_x = (u64 *) (sm_tw + 2 * (size_t) tw_words);         /* per group */
+	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;                 /* [hgroup][2^K] */
+	u64 *sm_x = (u64 *) (sm_tw + ((size_t) hgroup << K));        /* per group, NP tiles */
 
-	u64 u_begin, u_end;
-	cta_share(p.units, gridDim.x, blockIdx.x, u_begin, u_end);
-	if (u_begin >= u_end) {
-		return;
-	}
-
+	/* blockIdx.x -> (batch chunk, limb, H group) */
 	const unsigned hgroups = (1u << s0) >> p.hgroup_log2;
+	unsigned blk = blockIdx.x;
+	const unsigned hg = blk % hgroups;
+	blk /= hgroups;
+	const unsigned limb = blk % p.limbs;
+	const unsigned bc = blk / p.limbs;
 	const u64 batch = p.polys / p.limbs;
-	struct unit_info {
-		unsigned limb, H0, ntiles;
-		u64 b0;
-	};
-	auto decode = [&](u64 u) {
-		unit_info ui;
-		const unsigned hg = (unsigned) (u % hgroups);
-		const u64 r = u / hgroups;
-		ui.limb = (unsigned) (r % p.limbs);
-		ui.b0 = (r / p.limbs) * p.bchunk;
-		const u64 left = batch - ui.b0;
-		ui.ntiles = (unsigned) (left < p.bchunk ? left : p.bchunk) << p.hgroup_log2;
-		ui.H0 = hg << p.hgroup_log2;
-		return ui;
-	};
-	auto stage_twiddles = [&](const unit_info &ui, int buf) {
-		const ulonglong2 *tw_g = p.descs[ui.limb].tw + (INV ? ((u64) 1 << L) : 0);
-		for (unsigned v = threadIdx.x; v < tw_words; v += FAST_THREADS) {
-			const unsigned h = v >> K, node = v & ((1u << K) - 1);
-			if (node) {
-				const unsigned u = 31 - __clz(node);
-				const u64 root = ((u64) 1 << s0) + ui.H0 + h;
-				cp_async16(&sm_tw[(size_t) buf * tw_words + v],
-						&tw_g[(root << u) + (node - (1u << u))]);
-			}
-		}
-		cp_async_commit();
-	};
+	const u64 b0 = (u64) bc * p.bchunk;
+	const unsigned nb = (unsigned) (batch - b0 < p.bchunk ? batch - b0 : p.bchunk);
+	const unsigned H0 = hg << p.hgroup_log2;
+
+	const limb_desc &d = p.descs[limb];
+	const u64 q = d.q, twoq = 2 * q;
+	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H0, hgroup,
+			FAST_THREADS);
+	__syncthreads();
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int t = lane & (C::group - 1);                 /* thread within group */
 	const int slot = warp * C::groups_per_warp + (lane >> (K - 3));
-	u64 *xb = sm_x + (size_t) slot * C::xbuf;
+	u64 *xb = sm_x + (size_t) slot * (NP * C::xbuf);
 	constexpr int first = INV ? G::rounds - 1 : 0;
 	constexpr int last = INV ? 0 : G::rounds - 1;
 	const bool fold = INV && s0 == 0;
 	const bool canon = INV ? s0 == 0 : true;     /* pass with the final stage */
-
-	/* tiles of a unit: (b_local, h), h fastest; group `slot` takes every
-	 * groups_per_cta-th one.  Loop counts are uniform across the CTA. */
-	struct tile_ref {
-		bool active;
-		unsigned h;
-		u64 off;
-	};
-	auto locate = [&](const unit_info &ui, unsigned base) {
-		tile_ref tr;
-		const unsigned idx = base + slot;
-		tr.active = idx < ui.ntiles;
-		tr.h = idx & (hgroup - 1);
-		const u64 poly = (ui.b0 + (idx >> p.hgroup_log2)) * p.limbs + ui.limb;
-		tr.off = (poly << L) + ((u64) (ui.H0 + tr.h) << K);
-		return tr;
-	};
+	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
+	if (fold) {
+		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+		fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
+	}
 	/* per-thread bases; every access below is base + compile-time constant */
 	const int tb_first = G::tbase(first, t), tb_last = G::tbase(last, t);
-	auto load_tile = [&](const tile_ref &tr, u64 (&x)[8]) {
-		const u64 *sp = p.src + tr.off + tb_first;
+
+	/* work items of the CTA: (group of NP batch entries, h), h fastest; slot
+	 * `slot` takes every groups_per_cta-th one.  Uniform loop count. */
+	const unsigned nitems = ((nb + NP - 1) / NP) << p.hgroup_log2;
+	for (unsigned base = 0; base < nitems; base += C::groups_per_cta) {
+		const unsigned idx = base + slot;
+		const unsigned h = idx & (hgroup - 1), bg = idx >> p.hgroup_log2;
+		const ulonglong2 *twt = sm_tw + ((size_t) h << K);
+		bool active[NP];
+		u64 off[NP];
+		u64 x[NP][8];
 #pragma unroll
-		for (int e = 0; e < 8; e++) {
-			x[e] = tr.active ? sp[G::eoff(first, e)] : 0;
-		}
-	};
-
-	u64 u = u_begin;
-	unsigned base = 0;
-	unit_info cur = decode(u);
-	tile_ref tr_next = locate(cur, 0);
-	u64 x_next[8];
-	if (FAST_PREFETCH) {
-		load_tile(tr_next, x_next);
-	}
-	stage_twiddles(cur, 0);
-	int buf = 0;
-	u64 q = p.descs[cur.limb].q;
-	cp_async_wait_all();
-	__syncthreads();
-
-	while (true) {
-		u64 x[8];
-		const tile_ref tr = tr_next;
-		if (FAST_PREFETCH) {
+		for (int pp = 0; pp < NP; pp++) {
+			const unsigned bl = bg * NP + pp;
+			active[pp] = idx < nitems && bl < nb;
+			const u64 poly = (b0 + bl) * p.limbs + limb;
+			off[pp] = (poly << L) + ((u64) (H0 + h) << K);
+			const u64 *sp = p.src + off[pp] + tb_first;
 #pragma unroll
 			for (int e = 0; e < 8; e++) {
-				x[e] = x_next[e];
-			}
-		} else {
-			load_tile(tr, x);
-		}
-
-		/* where the following tile lives; start its loads now */
-		const bool unit_done = base + C::groups_per_cta >= cur.ntiles;
-		const bool more = !unit_done || u + 1 < u_end;
-		unit_info nxt = cur;
-		unsigned nbase = base + C::groups_per_cta;
-		if (unit_done && more) {
-			nxt = decode(u + 1);
-			nbase = 0;
-		}
-		if (base == 0 && u + 1 < u_end) {
-			stage_twiddles(decode(u + 1), buf ^ 1);
-		}
-		if (more) {
-			tr_next = locate(nxt, nbase);
-			if (FAST_PREFETCH) {
-				load_tile(tr_next, x_next);
+				x[pp][e] = active[pp] ? sp[G::eoff(first, e)] : 0;
 			}
 		}
-
-		const u64 twoq = 2 * q;
-		ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
-		if (fold) {
-			const limb_desc &d = p.descs[cur.limb];
-			fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
-			fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
-		}
-		const ulonglong2 *twt = sm_tw + (size_t) buf * tw_words + ((size_t) tr.h << K);
 
 #pragma unroll
 		for (int rr = 0; rr < G::rounds; rr++) {
 			const int r = INV ? G::rounds - 1 - rr : rr;
 			if (rr > 0) {
-				/* redistribute: previous round's layout -> this round's.
-				 * xpad is additive over the disjoint thread / register bits */
+				/* redistribute: previous round's layout -> this round's */
 				const int prev = INV ? r + 1 : r - 1;
 				u64 *xw = xb + xpad(G::tbase(prev, t));
 #pragma unroll
-				for (int e = 0; e < 8; e++) {
-					xw[xpad(G::eoff(prev, e))] = x[e];
+				for (int pp = 0; pp < NP; pp++) {
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						xw[pp * C::xbuf + xpad(G::eoff(prev, e))] = x[pp][e];
+					}
 				}
 				__syncwarp();
 				const u64 *xr = xb + xpad(G::tbase(r, t));
 #pragma unroll
-				for (int e = 0; e < 8; e++) {
-					x[e] = xr[xpad(G::eoff(r, e))];
+				for (int pp = 0; pp < NP; pp++) {
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						x[pp][e] = xr[pp * C::xbuf + xpad(G::eoff(r, e))];
+					}
 				}
 			}
 			if (fold) {
-				tile_round<K, INV, true>(x, r, t, twt, q, twoq, fold_a, fold_b);
+				tile_round<K, INV, true, NP>(x, r, t, twt, q, twoq, fold_a, fold_b);
 			} else {
-				tile_round<K, INV, false>(x, r, t, twt, q, twoq, fold_a, fold_b);
+				tile_round<K, INV, false, NP>(x, r, t, twt, q, twoq, fold_a, fold_b);
 			}
 		}
-		__syncwarp();
+		__syncwarp();   /* the exchange buffer is reused by the next item */
 
-		if (tr.active) {
-			u64 *dp = p.dst + tr.off + tb_last;
 #pragma unroll
-			for (int e = 0; e < 8; e++) {
-				u64 v = x[e];
-				if (canon) {
-					if (!INV) {
-						v = csub(v, twoq);
+		for (int pp = 0; pp < NP; pp++) {
+			if (active[pp]) {
+				u64 *dp = p.dst + off[pp] + tb_last;
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					u64 v = x[pp][e];
+					if (canon) {
+						if (!INV) {
+							v = csub(v, twoq);
+						}
+						v = csub(v, q);
 					}
-					v = csub(v, q);
+					dp[G::eoff(last, e)] = v;
 				}
-				dp[G::eoff(last, e)] = v;
 			}
-		}
-
-		if (!more) {
-			break;
-		}
-		if (unit_done) {
-			/* next unit: its twiddles have been streaming into buf^1 */
-			cp_async_wait_all();
-			__syncthreads();
-			buf ^= 1;
-			u++;
-			cur = nxt;
-			base = 0;
-			q = p.descs[cur.limb].q;
-		} else {
-			base = nbase;
 		}
 	}
 }
 
-/* Column pass.  Work unit = (poly, H, column group): one tile group of 2^K rows
- * at stride 2^(L-s0-K) by 2^CL adjacent columns.  threads = 2^(K-3) row groups
- * x 2^CL columns, lanes along the columns.  Persistent grid, contiguous unit
- * ranges, next unit prefetched into registers, twiddles double-buffered. */
-template <int K, int CL>
+/* Column pass.  CTA = (poly, H, column group): one tile group of 2^K rows at
+ * stride 2^(L-s0-K) by 2^CL adjacent columns.  thread = (row group, NP adjacent
+ * columns), lanes along the columns: every global access is a run of 2^CL * 8
+ * contiguous bytes (128-bit per thread for NP = 2) and every shared-memory
+ * access is conflict-free without padding. */
+template <int K, int CL, int NP>
 struct col_cfg {
-	static constexpr int cols_log2 = CL;
+	static constexpr int cthreads_log2 = CL - (NP == 2 ? 1 : 0);
+	static constexpr int threads = 1 << (K - 3 + cthreads_log2);
 	static constexpr int cols = 1 << CL;
-	static constexpr int threads = 1 << (K - 3 + CL);
 };
 
-template <bool INV, int K, int CL>
-__global__ void __launch_bounds__(1 << (K - 3 + CL),
-		COLS_MIN_THREADS >> (K - 3 + CL))
+template <int NP> struct col_vec;
+template <> struct col_vec<1> { typedef u64 type; };
+template <> struct col_vec<2> { typedef ulonglong2 type; };
+
+template <bool INV, int K, int CL, int NP>
+__global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
+		(NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
+			>> (K - 3 + CL - (NP == 2 ? 1 : 0)))
 ntt_cols_kernel(const fast_pass p) {
 	using G = tile_geom<K>;
-	using C = col_cfg<K, CL>;
+	using C = col_cfg<K, CL, NP>;
+	typedef typename col_vec<NP>::type vec_t;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;           /* [2][2^K] */
-	u64 *sm_x = (u64 *) (sm_tw + (2 << K));                /* [2^K][COLS] */
+	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;           /* [2^K] */
+	u64 *sm_x = (u64 *) (sm_tw + (1 << K));                /* [2^K][2^CL] */
 
 	const unsigned L = p.log2n, s0 = p.s0;
 	const unsigned low_bits = L - s0 - K;                  /* log2 of the row stride */
-	const unsigned cgroups_log2 = low_bits - C::cols_log2;
+	const unsigned cgroups_log2 = low_bits - CL;
 
-	u64 u_begin, u_end;
-	cta_share(p.units, gridDim.x, blockIdx.x, u_begin, u_end);
-	if (u_begin >= u_end) {
-		return;
-	}
+	/* blockIdx.x -> (poly, H, column group), column group fastest */
+	u64 blk = blockIdx.x;
+	const u64 cg = blk & (((u64) 1 << cgroups_log2) - 1);
+	blk >>= cgroups_log2;
+	const u64 H = blk & (((u64) 1 << s0) - 1);
+	const u64 poly = blk >> s0;
 
-	const int c = threadIdx.x & (C::cols - 1);
-	const int t = threadIdx.x >> C::cols_log2;             /* row group */
+	const limb_desc &d = p.descs[poly % p.limbs];
+	const u64 q = d.q, twoq = 2 * q;
+
+	const int c = (threadIdx.x & ((1 << C::cthreads_log2) - 1)) * NP;
+	const int t = threadIdx.x >> C::cthreads_log2;         /* row group */
 	constexpr int first = INV ? G::rounds - 1 : 0;
 	constexpr int last = INV ? 0 : G::rounds - 1;
+	const u64 base = (poly << L) + (H << (L - s0)) + (cg << CL) + c;
+
+	u64 x[NP][8];
+	{
+		const u64 *sp = p.src + base + ((u64) G::tbase(first, t) << low_bits);
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			const vec_t v = *(const vec_t *) (sp + ((u64) G::eoff(first, e) << low_bits));
+			if (NP == 2) {
+				x[0][e] = ((const u64 *) &v)[0];
+				x[NP - 1][e] = ((const u64 *) &v)[NP - 1];
+			} else {
+				x[0][e] = ((const u64 *) &v)[0];
+			}
+		}
+	}
+	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
+			C::threads);
 	const bool fold = INV && s0 == 0;
 	/* the forward transform always ends in a row pass; the inverse ends here
 	 * when this pass holds stage 0 */
 	const bool canon = INV && s0 == 0;
-
-	struct unit_info {
-		unsigned limb;
-		u64 H, base;
-	};
-	/* unit -> (poly, H, column group), column group fastest */
-	auto decode = [&](u64 u) {
-		unit_info ui;
-		const u64 cg = u & (((u64) 1 << cgroups_log2) - 1);
-		const u64 r = u >> cgroups_log2;
-		ui.H = r & (((u64) 1 << s0) - 1);
-		const u64 poly = r >> s0;
-		ui.limb = (unsigned) (poly % p.limbs);
-		ui.base = (poly << L) + (ui.H << (L - s0)) + (cg << C::cols_log2) + c;
-		return ui;
-	};
-	auto stage_twiddles = [&](const unit_info &ui, int buf) {
-		const ulonglong2 *tw_g = p.descs[ui.limb].tw + (INV ? ((u64) 1 << L) : 0);
-		for (unsigned node = threadIdx.x; node < (1u << K); node += C::threads) {
-			if (node) {
-				const unsigned u = 31 - __clz(node);
-				const u64 root = ((u64) 1 << s0) + ui.H;
-				cp_async16(&sm_tw[(buf << K) + node],
-						&tw_g[(root << u) + (node - (1u << u))]);
-			}
-		}
-		cp_async_commit();
-	};
-	const int tb_first = G::tbase(first, t), tb_last = G::tbase(last, t);
-	auto load_unit = [&](const unit_info &ui, u64 (&x)[8]) {
-		const u64 *sp = p.src + ui.base + ((u64) tb_first << low_bits);
-#pragma unroll
-		for (int e = 0; e < 8; e++) {
-			x[e] = sp[(u64) G::eoff(first, e) << low_bits];
-		}
-	};
-
-	unit_info cur = decode(u_begin);
-	u64 x_next[8];
-	if (FAST_PREFETCH) {
-		load_unit(cur, x_next);
+	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
+	if (fold) {
+		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+		fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
 	}
-	stage_twiddles(cur, 0);
-	int buf = 0;
-	u64 q = p.descs[cur.limb].q;
-	cp_async_wait_all();
-	__syncthreads();
+	__syncthreads();   /* twiddles staged */
 
-	for (u64 u = u_begin; u < u_end; u++) {
-		u64 x[8];
-		if (FAST_PREFETCH) {
+#pragma unroll
+	for (int rr = 0; rr < G::rounds; rr++) {
+		const int r = INV ? G::rounds - 1 - rr : rr;
+		if (rr > 0) {
+			const int prev = INV ? r + 1 : r - 1;
+			u64 *xw = sm_x + (G::tbase(prev, t) << CL) + c;
 #pragma unroll
 			for (int e = 0; e < 8; e++) {
-				x[e] = x_next[e];
-			}
-		} else {
-			load_unit(cur, x);
-		}
-		unit_info nxt = cur;
-		bool flip = false;
-		if (u + 1 < u_end) {
-			nxt = decode(u + 1);
-			flip = nxt.limb != cur.limb || nxt.H != cur.H;
-			if (flip) {
-				stage_twiddles(nxt, buf ^ 1);
-			}
-			if (FAST_PREFETCH) {
-				load_unit(nxt, x_next);
-			}
-		}
-
-		const u64 twoq = 2 * q;
-		ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
-		if (fold) {
-			const limb_desc &d = p.descs[cur.limb];
-			fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
-			fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
-		}
-		const ulonglong2 *twt = sm_tw + (buf << K);
-
-#pragma unroll
-		for (int rr = 0; rr < G::rounds; rr++) {
-			const int r = INV ? G::rounds - 1 - rr : rr;
-			if (rr > 0) {
-				const int prev = INV ? r + 1 : r - 1;
-				u64 *xw = sm_x + (G::tbase(prev, t) << C::cols_log2) + c;
-#pragma unroll
-				for (int e = 0; e < 8; e++) {
-					xw[G::eoff(prev, e) << C::cols_log2] = x[e];
+				vec_t v;
+				((u64 *) &v)[0] = x[0][e];
+				if (NP == 2) {
+					((u64 *) &v)[NP - 1] = x[NP - 1][e];
 				}
-				__syncthreads();
-				const u64 *xr = sm_x + (G::tbase(r, t) << C::cols_log2) + c;
-#pragma unroll
-				for (int e = 0; e < 8; e++) {
-					x[e] = xr[G::eoff(r, e) << C::cols_log2];
-				}
+				*(vec_t *) (xw + (G::eoff(prev, e) << CL)) = v;
 			}
-			if (fold) {
-				tile_round<K, INV, true>(x, r, t, twt, q, twoq, fold_a, fold_b);
-			} else {
-				tile_round<K, INV, false>(x, r, t, twt, q, twoq, fold_a, fold_b);
-			}
-		}
-
-		u64 *dp = p.dst + cur.base + ((u64) tb_last << low_bits);
-#pragma unroll
-		for (int e = 0; e < 8; e++) {
-			u64 v = x[e];
-			if (canon) {
-				v = csub(v, q);
-			}
-			dp[(u64) G::eoff(last, e) << low_bits] = v;
-		}
-
-		if (u + 1 < u_end) {
-			/* the exchange buffer is reused by the next unit, and its
-			 * twiddles (if they differ) must have landed */
-			cp_async_wait_all();
 			__syncthreads();
-			if (flip) {
-				buf ^= 1;
-				q = p.descs[nxt.limb].q;
+			const u64 *xr = sm_x + (G::tbase(r, t) << CL) + c;
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				const vec_t v = *(const vec_t *) (xr + (G::eoff(r, e) << CL));
+				x[0][e] = ((const u64 *) &v)[0];
+				if (NP == 2) {
+					x[NP - 1][e] = ((const u64 *) &v)[NP - 1];
+				}
 			}
-			cur = nxt;
+		}
+		if (fold) {
+			tile_round<K, INV, true, NP>(x, r, t, sm_tw, q, twoq, fold_a, fold_b);
+		} else {
+			tile_round<K, INV, false, NP>(x, r, t, sm_tw, q, twoq, fold_a, fold_b);
 		}
 	}
+
+	u64 *dp = p.dst + base + ((u64) G::tbase(last, t) << low_bits);
+#pragma unroll
+	for (int e = 0; e < 8; e++) {
+		vec_t v;
+#pragma unroll
+		for (int pp = 0; pp < NP; pp++) {
+			u64 w = x[pp][e];
+			if (canon) {
+				w = csub(w, q);
+			}
+			((u64 *) &v)[pp] = w;
+		}
+		*(vec_t *) (dp + ((u64) G::eoff(last, e) << low_bits)) = v;
+	}
 }
 
-/* persistent grid: resident CTAs per SM x SM count, capped by the unit count */
-template <class Kernel>
-static unsigned persistent_grid(struct vkhel_ctx *ctx, Kernel kernel,
-		int threads, size_t smem, u64 units) {
-	int per_sm = 0;
-	CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
-				threads, smem));
-	if (per_sm < 1) {
-		per_sm = 1;
-	}
-	const u64 resident = (u64) per_sm * ctx->dev.sm_count;
-	if (!FAST_PERSISTENT) {
-		const u64 ctas = (units + FAST_UNITS_PER_CTA - 1) / FAST_UNITS_PER_CTA;
-		VK_REQUIRE(ctas <= 0x7fffffffull, "transform too large for one launch");
-		return (unsigned) ctas;
-	}
-	return (unsigned) (units < resident ? units : resident);
-}
-
-template <bool INV, int K>
-static void run_rows(struct vkhel_ctx *ctx, fast_pass p) {
+template <bool INV, int K, int NP>
+static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	using C = row_cfg<K>;
 	const u64 batch = p.polys / p.limbs;
-	/* enough tiles per unit to occupy every warp-group: H values first (they
+	const u64 slots = (u64) C::groups_per_cta * NP;   /* tiles in flight per CTA */
+	/* enough tiles per CTA to occupy every warp-group: H values first (they
 	 * are contiguous in memory), then batch entries */
 	unsigned hgroup_log2 = 0;
 	while ((1u << hgroup_log2) < (unsigned) C::groups_per_cta
 			&& hgroup_log2 < p.s0
-			&& ((u64) batch << hgroup_log2) < (u64) C::groups_per_cta) {
+			&& ((u64) (batch + NP - 1) / NP << hgroup_log2) < (u64) C::groups_per_cta) {
 		hgroup_log2++;
 	}
-	/* two rounds of tiles per unit amortise the twiddle staging and the CTA
-	 * barrier at the unit boundary */
-	u64 bchunk = (2 * (u64) C::groups_per_cta) >> hgroup_log2;
-	if (bchunk < 1) {
-		bchunk = 1;
+	/* two rounds of items per CTA amortise the twiddle staging */
+	u64 bchunk = (2 * slots) >> hgroup_log2;
+	if (bchunk < (u64) NP) {
+		bchunk = NP;
 	}
 	if (bchunk > batch) {
 		bchunk = batch;
@@ -731,47 +587,73 @@ static void run_rows(struct vkhel_ctx *ctx, fast_pass p) {
 	p.hgroup_log2 = hgroup_log2;
 	p.bchunk = (unsigned) bchunk;
 	const u64 bchunks = (batch + bchunk - 1) / bchunk;
-	p.units = bchunks * p.limbs * ((1ull << p.s0) >> hgroup_log2);
-	const size_t smem = 2 * ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
-		+ (size_t) C::groups_per_cta * C::xbuf * sizeof(u64);
+	const u64 blocks = bchunks * p.limbs * ((1ull << p.s0) >> hgroup_log2);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
+	const size_t smem = ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
+		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
 	if (smem > 48 * 1024) {
 		/* per device, and cheap: set it on every such launch */
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K>,
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	const unsigned grid = persistent_grid(ctx, ntt_rows_kernel<INV, K>,
-			FAST_THREADS, smem, p.units);
-	ntt_rows_kernel<INV, K><<<grid, FAST_THREADS, smem, ctx_stream(ctx)>>>(p);
+	ntt_rows_kernel<INV, K, NP><<<(unsigned) blocks, FAST_THREADS, smem,
+		ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	ctx->dev.launches++;
 }
 
-template <bool INV, int K, int CL>
-static void run_cols_cl(struct vkhel_ctx *ctx, fast_pass p) {
-	using C = col_cfg<K, CL>;
+template <bool INV, int K>
+static void run_rows(struct vkhel_ctx *ctx, const fast_pass &p) {
+	/* two batch entries per thread when there are two to pair up */
+	if constexpr (ROWS_NP == 2) {
+		if (p.polys / p.limbs >= 2) {
+			run_rows_np<INV, K, 2>(ctx, p);
+			return;
+		}
+	}
+	run_rows_np<INV, K, 1>(ctx, p);
+}
+
+template <bool INV, int K, int CL, int NP>
+static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
+	using C = col_cfg<K, CL, NP>;
 	const unsigned low_bits = p.log2n - p.s0 - K;
 	VK_REQUIRE(low_bits >= (unsigned) CL,
 			"internal: column pass narrower than its CTA");
-	p.units = (p.polys << p.s0) << (low_bits - CL);
-	const size_t smem = 2 * (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
-	const unsigned grid = persistent_grid(ctx, ntt_cols_kernel<INV, K, CL>,
-			C::threads, smem, p.units);
-	ntt_cols_kernel<INV, K, CL><<<grid, C::threads, smem, ctx_stream(ctx)>>>(p);
+	const u64 blocks = (p.polys << p.s0) << (low_bits - CL);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
+	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
+	if (smem > 48 * 1024) {
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel<INV, K, CL, NP>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
+	ntt_cols_kernel<INV, K, CL, NP><<<(unsigned) blocks, C::threads, smem,
+		ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	ctx->dev.launches++;
 }
 
-/* 256 threads per CTA, i.e. 2^(11-K) columns; the 8-point column pass of
- * n = 2^9 and 2^10 has only 64 / 128 columns to offer */
+/* 256 threads per CTA: 2^(12-K) columns with two columns per thread, 2^(11-K)
+ * with one; the 8-point column pass of n = 2^9 and 2^10 has only 64 / 128
+ * columns to offer and runs with fewer threads */
 template <bool INV, int K>
 static void run_cols(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const unsigned low_bits = p.log2n - p.s0 - K;
-	if (K == 3 && low_bits == 6) {
-		run_cols_cl<INV, 3, 6>(ctx, p);
+	if constexpr (COLS_NP == 2) {
+		if (low_bits >= 12 - K) {
+			run_cols_cl<INV, K, 12 - K, 2>(ctx, p);
+			return;
+		}
+	}
+	if (low_bits >= 11 - K) {
+		run_cols_cl<INV, K, 11 - K, 1>(ctx, p);
 	} else if (K == 3 && low_bits == 7) {
-		run_cols_cl<INV, 3, 7>(ctx, p);
+		run_cols_cl<INV, 3, 7, 1>(ctx, p);
+	} else if (K == 3 && low_bits == 6) {
+		run_cols_cl<INV, 3, 6, 1>(ctx, p);
 	} else {
-		run_cols_cl<INV, K, 11 - K>(ctx, p);
+		VK_DIE("internal: no column kernel for K=%d, row stride 2^%u", K,
+				low_bits);
 	}
 }
 
@@ -833,7 +715,6 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	p.polys = polys;
 	p.hgroup_log2 = 0;
 	p.bchunk = 1;
-	p.units = 0;
 
 	gen_pass lead;
 	lead.descs = descs;

@@ -20,6 +20,12 @@
  * with t the thread's number inside its group and e = 0..7 the register.
  * The inverse direction walks the same rounds and stages backwards.
  *
+ * A thread may carry NP = 2 such tiles at once when they share their twiddles
+ * (two batch entries of one limb, or two adjacent columns): the shared-memory
+ * twiddle fetch, the dominant non-arithmetic cost (tools/bfly_bench.cu: 2.46
+ * butterflies/clk/SM with an LDS.128 per butterfly against 2.85 without), is
+ * then paid once per two butterflies.
+ *
  * Arithmetic: Harvey lazy butterflies (modarith.cuh).  Forward values stay in
  * [0,4q), inverse values in [0,2q); q < 2^62.
  */
@@ -79,12 +85,14 @@ struct tile_geom {
 	}
 };
 
-/* One round of butterflies on x[0..7].
+/* One round of butterflies on NP interleaved tiles x[p][0..7] that share their
+ * twiddles (NP batch entries of the same limb and tile position, or NP adjacent
+ * columns): every (w, w') pair fetched from shared memory feeds NP butterflies.
  *   twt: the tile's twiddle subtree in shared memory, twt[node] = (w, w')
  *   FOLD: inverse only -- local stage 0 is global stage 0: multiply by n^-1
  *         (fold_a = n^-1, fold_b = inv_root[1] * n^-1) instead of node 1. */
-template <int K, bool INV, bool FOLD>
-__device__ __forceinline__ void tile_round(u64 (&x)[8], int r, int t,
+template <int K, bool INV, bool FOLD, int NP>
+__device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 		const ulonglong2 *twt, u64 q, u64 twoq, ulonglong2 fold_a,
 		ulonglong2 fold_b) {
 	using G = tile_geom<K>;
@@ -103,19 +111,27 @@ __device__ __forceinline__ void tile_round(u64 (&x)[8], int r, int t,
 			if (e & (1 << beta)) {
 				continue;
 			}
-			u64 &X = x[e];
-			u64 &Y = x[e | (1 << beta)];
 			if (INV && FOLD && u == 0) {
-				const u64 s = X + Y;
-				const u64 d = X - Y + twoq;
-				X = shoup_lazy(s, fold_a.x, fold_a.y, q);
-				Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
+#pragma unroll
+				for (int p = 0; p < NP; p++) {
+					u64 &X = x[p][e];
+					u64 &Y = x[p][e | (1 << beta)];
+					const u64 s = X + Y;
+					const u64 d = X - Y + twoq;
+					X = shoup_lazy(s, fold_a.x, fold_a.y, q);
+					Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
+				}
 			} else {
 				const ulonglong2 w = twp[G::goff(r, j, e)];
-				if (INV) {
-					gs_lazy(X, Y, w.x, w.y, q, twoq);
-				} else {
-					ct_lazy(X, Y, w.x, w.y, q, twoq);
+#pragma unroll
+				for (int p = 0; p < NP; p++) {
+					u64 &X = x[p][e];
+					u64 &Y = x[p][e | (1 << beta)];
+					if (INV) {
+						gs_lazy(X, Y, w.x, w.y, q, twoq);
+					} else {
+						ct_lazy(X, Y, w.x, w.y, q, twoq);
+					}
 				}
 			}
 		}

@@ -18,8 +18,38 @@ static void enter(const struct vkhel_ctx *ctx) {
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
 }
 
+/* Device pointer of a vector for an operation on the compute stream.  If an
+ * asynchronous upload/download of this vector is still in flight on a copy
+ * stream, the compute stream is made to wait for it first (once). */
 static inline u64 *dev_u64(const struct vkhel_vector *v) {
+	if (v->xfer_pending) {
+		struct vkhel_vector *vec = (struct vkhel_vector *) v;
+		CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(vec->ctx),
+					(cudaEvent_t) vec->xfer_event, 0));
+		vec->xfer_pending = 0;
+	}
 	return (u64 *) v->device.ptr;
+}
+
+/* start a transfer of `vec` on copy stream `copy`: it must come after all
+ * compute enqueued so far and after the previous transfer of this vector */
+static void xfer_begin(struct vkhel_vector *vec, cudaStream_t copy) {
+	struct vkhel_ctx *ctx = vec->ctx;
+	cudaEvent_t fork = (cudaEvent_t) ctx->dev.ev_scratch;
+	CUDA_CHECK(cudaEventRecord(fork, ctx_stream(ctx)));
+	CUDA_CHECK(cudaStreamWaitEvent(copy, fork, 0));
+	if (!vec->xfer_event) {
+		cudaEvent_t ev;
+		CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		vec->xfer_event = ev;
+	} else {
+		CUDA_CHECK(cudaStreamWaitEvent(copy, (cudaEvent_t) vec->xfer_event, 0));
+	}
+}
+
+static void xfer_end(struct vkhel_vector *vec, cudaStream_t copy) {
+	CUDA_CHECK(cudaEventRecord((cudaEvent_t) vec->xfer_event, copy));
+	vec->xfer_pending = 1;
 }
 
 /* ---- lifecycle ---------------------------------------------------------------- */
@@ -56,9 +86,13 @@ extern "C" void vkhel_vector_destroy(struct vkhel_vector *vec) {
 		 * written back */
 		pinned_release(ctx, vec->host.ptr);
 	}
-	/* stream-ordered free: work already enqueued on the stream completes
-	 * before the block is reused */
+	/* stream-ordered free: work already enqueued on the stream (and any
+	 * transfer still in flight) completes before the block is reused */
+	(void) dev_u64(vec);
 	device_free(ctx, vec->device.ptr);
+	if (vec->xfer_event) {
+		CUDA_CHECK(cudaEventDestroy((cudaEvent_t) vec->xfer_event));
+	}
 	free(vec);
 }
 
@@ -67,7 +101,7 @@ extern "C" struct vkhel_vector *vkhel_vector_dup(struct vkhel_vector *src) {
 	struct vkhel_vector *dup = vkhel_vector_create2(src->ctx, src->length,
 			false);
 	if (src->length) {
-		CUDA_CHECK(cudaMemcpyAsync(dup->device.ptr, src->device.ptr,
+		CUDA_CHECK(cudaMemcpyAsync(dup->device.ptr, dev_u64(src),
 					src->device.bytes, cudaMemcpyDeviceToDevice,
 					ctx_stream(src->ctx)));
 	}
@@ -84,7 +118,7 @@ extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 		return;
 	}
 	enter(vec->ctx);
-	CUDA_CHECK(cudaMemcpyAsync(vec->device.ptr, elements, vec->device.bytes,
+	CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec), elements, vec->device.bytes,
 				cudaMemcpyHostToDevice, ctx_stream(vec->ctx)));
 	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
 }
@@ -99,7 +133,7 @@ extern "C" void vkhel_vector_map(struct vkhel_vector *vec, void **mem,
 	vec->host.bytes = vec->device.bytes;
 	vec->host.ptr = pinned_acquire(vec->ctx, vec->host.bytes);
 	if (vec->length) {
-		CUDA_CHECK(cudaMemcpyAsync(vec->host.ptr, vec->device.ptr,
+		CUDA_CHECK(cudaMemcpyAsync(vec->host.ptr, dev_u64(vec),
 					vec->device.bytes, cudaMemcpyDeviceToHost,
 					ctx_stream(vec->ctx)));
 	}
@@ -113,7 +147,7 @@ extern "C" void vkhel_vector_unmap(struct vkhel_vector *vec) {
 	enter(vec->ctx);
 	/* the whole vector is written back (reference vector.c:291) */
 	if (vec->length) {
-		CUDA_CHECK(cudaMemcpyAsync(vec->device.ptr, vec->host.ptr,
+		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec), vec->host.ptr,
 					vec->device.bytes, cudaMemcpyHostToDevice,
 					ctx_stream(vec->ctx)));
 		/* the staging buffer goes back to the cache: finish the copy first */
@@ -141,28 +175,38 @@ extern "C" uint64_t vkhel_vector_length(const struct vkhel_vector *vec) {
 }
 
 extern "C" void *vkhel_vector_device_ptr(struct vkhel_vector *vec) {
-	return vec->device.ptr;
+	return dev_u64(vec);
 }
 
+/* Asynchronous transfers run on the context's two copy streams, so that an
+ * upload, kernels and a download of different vectors overlap (PCIe is full
+ * duplex).  Ordering: a transfer starts after all compute enqueued before the
+ * call and after the previous transfer of the same vector; the next operation
+ * that touches the vector waits for the transfer (dev_u64). */
 extern "C" void vkhel_vector_upload(struct vkhel_vector *vec,
 		const uint64_t *src, uint64_t offset, uint64_t count) {
 	VK_REQUIRE(offset + count <= vec->length, "upload out of range");
 	enter(vec->ctx);
 	if (count) {
-		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec) + offset, src,
-					count * sizeof(uint64_t), cudaMemcpyHostToDevice,
-					ctx_stream(vec->ctx)));
+		cudaStream_t copy = (cudaStream_t) vec->ctx->dev.stream_h2d;
+		xfer_begin(vec, copy);
+		CUDA_CHECK(cudaMemcpyAsync((u64 *) vec->device.ptr + offset, src,
+					count * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
+		xfer_end(vec, copy);
 	}
 }
 
-extern "C" void vkhel_vector_download(const struct vkhel_vector *vec,
+extern "C" void vkhel_vector_download(const struct vkhel_vector *cvec,
 		uint64_t *dst, uint64_t offset, uint64_t count) {
+	struct vkhel_vector *vec = (struct vkhel_vector *) cvec;
 	VK_REQUIRE(offset + count <= vec->length, "download out of range");
 	enter(vec->ctx);
 	if (count) {
-		CUDA_CHECK(cudaMemcpyAsync(dst, dev_u64(vec) + offset,
-					count * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-					ctx_stream(vec->ctx)));
+		cudaStream_t copy = (cudaStream_t) vec->ctx->dev.stream_d2h;
+		xfer_begin(vec, copy);
+		CUDA_CHECK(cudaMemcpyAsync(dst, (u64 *) vec->device.ptr + offset,
+					count * sizeof(uint64_t), cudaMemcpyDeviceToHost, copy));
+		xfer_end(vec, copy);
 	}
 }
 
