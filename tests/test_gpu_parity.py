@@ -288,6 +288,21 @@ def test_ntt_random_large(ctx, log2n):
         tp.destroy()
 
 
+@pytest.mark.parametrize("log2n", [18, 19, 20])
+def test_ntt_random_huge(ctx, log2n):
+    """n = 2^18: 1024-point column tiles; n > 2^18: leading strided pass.
+    Q61 = 2^61 - 2^21 + 1 is the only KAT modulus with enough 2-adicity."""
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    tp = TablePair(n, params.Q61)
+    x = rand_mod(rng, n, tp.q)
+    fwd = run_forward(ctx, x, tp)
+    assert np.array_equal(fwd, oracle.forward(x, tp.ora))
+    assert np.array_equal(run_inverse(ctx, fwd, tp, in_place=True), x)
+    assert np.array_equal(run_inverse(ctx, x, tp), oracle.inverse(x, tp.ora))
+    tp.destroy()
+
+
 def test_inverse_scales_tail_like_reference(ctx):
     """result longer than n: the reference multiplies the tail by n^-1 too
     (SURVEY App. B, Q4); the forward transform leaves the tail alone"""

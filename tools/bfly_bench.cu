@@ -22,6 +22,9 @@ typedef unsigned int u32;
 	fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 struct consts { u64 q, twoq, w, wp; };
+struct fp_consts { double dp0, c0, dp1, c1; };
+struct tw48 { unsigned long long w, wp; fp_consts f; };
+__device__ __forceinline__ fp_consts make_fp(unsigned long long wp);
 __shared__ ulonglong2 sm_tw[256];
 
 template <class B>
@@ -33,6 +36,13 @@ __global__ void __launch_bounds__(1024) bench(u64 *sink, u64 *cycles, consts c, 
 		y[i] = (c.q >> 2) + threadIdx.x * 131 + 7 * i;
 	}
 	if (threadIdx.x < 256) sm_tw[threadIdx.x] = make_ulonglong2(c.w + threadIdx.x, c.wp - threadIdx.x);
+	{
+		extern __shared__ tw48 sm48[];
+		if (threadIdx.x < 128) {
+			tw48 tw; tw.w = c.w + threadIdx.x; tw.wp = c.wp - threadIdx.x; tw.f = make_fp(tw.wp);
+			sm48[threadIdx.x] = tw;
+		}
+	}
 	__syncthreads();
 	const u64 t0 = clock64();
 #pragma unroll 1
@@ -159,6 +169,51 @@ struct ct_v9 { static const char *name() { return "CT v9 harvey, w/w' LDS.128 pe
 		x = xr + t; y = xr - t + c.twoq;
 	} };
 
+/* ---- V10: quotient estimate with the two cross products on the FP64 pipe ----
+ * hi32(a*b) for 32-bit a, b is the low mantissa word of fma_rz(a, b, 2^84).
+ * With A = 2^52 + a (bit pattern 0x43300000:a) and c = 2^84 - 2^52*b
+ * precomputed per twiddle, fma_rz(A, b, c) = a*b + 2^84 exactly, so neither
+ * operand needs a conversion.  h' = y1*p1 + hi32(y1*p0) + hi32(y0*p1) is in
+ * [hi-2, hi]  =>  t in [0,4q), values in [0,8q), one csub(x, 4q). */
+__device__ __forceinline__ u64 mulhi_fp64(u64 y, u64 wp, const fp_consts &f) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), p1 = (u32) (wp >> 32);
+	const double A0 = __hiloint2double(0x43300000, (int) y0);
+	const double A1 = __hiloint2double(0x43300000, (int) y1);
+	const u32 k0 = (u32) __double2loint(__fma_rz(A1, f.dp0, f.c0)); /* hi32(y1*p0) */
+	const u32 k1 = (u32) __double2loint(__fma_rz(A0, f.dp1, f.c1)); /* hi32(y0*p1) */
+	return (u64) y1 * p1 + k0 + k1;
+}
+__device__ __forceinline__ fp_consts make_fp(u64 wp) {
+	fp_consts f;
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32);
+	f.dp0 = (double) p0; f.c0 = 0x1p84 - 0x1p52 * (double) p0;
+	f.dp1 = (double) p1; f.c1 = 0x1p84 - 0x1p52 * (double) p1;
+	return f;
+}
+struct ct_v10 { static const char *name() { return "CT v10 fp64 cross products, csub(x,4q), uniform tw"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const fp_consts f = make_fp(c.wp);
+		const u64 fourq = 2 * c.twoq;
+		const u64 xr = csub(x, fourq);
+		const u64 t = y * c.w - mulhi_fp64(y, c.wp, f) * c.q;
+		x = xr + t; y = xr - t + fourq;
+	} };
+struct ct_v11 { static const char *name() { return "CT v11 fp64 cross products, 48-byte twiddle from smem"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		extern __shared__ tw48 sm48[];
+		const tw48 tw = sm48[(threadIdx.x + (unsigned) x) & 127];
+		const u64 fourq = 2 * c.twoq;
+		const u64 xr = csub(x, fourq);
+		const u64 t = y * tw.w - mulhi_fp64(y, tw.wp, tw.f) * c.q;
+		x = xr + t; y = xr - t + fourq;
+	} };
+struct only_dfma { static const char *name() { return "2x DFMA only (fp64 pipe rate; per pair)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		double a = __longlong_as_double((long long) x), b = __longlong_as_double((long long) y);
+		a = __fma_rz(a, 1.0000001, b); b = __fma_rz(b, 0.9999999, a);
+		x = (u64) __double_as_longlong(a); y = (u64) __double_as_longlong(b);
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -208,7 +263,7 @@ static void run(int sms, const consts &c) {
 	CHECK(cudaMalloc(&sink, 8));
 	CHECK(cudaMalloc(&cycles, sms * sizeof(u64)));
 	for (int rep = 0; rep < 2; rep++) {
-		bench<<<sms, g_threads>>>(sink, cycles, c, B());
+		bench<<<sms, g_threads, 128 * 48>>>(sink, cycles, c, B());
 		CHECK(cudaDeviceSynchronize());
 	}
 	std::vector<u64> h(sms);
@@ -238,7 +293,7 @@ int main() {
 		run<ct_v0>(sms, c);
 	}
 	g_threads = 1024;
-	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v10>(sms, c); run<ct_v11>(sms, c); run<only_dfma>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);

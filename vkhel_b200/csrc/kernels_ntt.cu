@@ -457,8 +457,10 @@ template <> struct col_vec<2> { typedef ulonglong2 type; };
 
 template <bool INV, int K, int CL, int NP>
 __global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
-		(NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
-			>> (K - 3 + CL - (NP == 2 ? 1 : 0)))
+		((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
+			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) > 0
+		? ((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
+			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) : 1)
 ntt_cols_kernel(const fast_pass p) {
 	using G = tile_geom<K>;
 	using C = col_cfg<K, CL, NP>;
@@ -639,13 +641,17 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 template <bool INV, int K>
 static void run_cols(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const unsigned low_bits = p.log2n - p.s0 - K;
-	if constexpr (COLS_NP == 2) {
+	if constexpr (COLS_NP == 2 && K <= 8) {
 		if (low_bits >= 12 - K) {
 			run_cols_cl<INV, K, 12 - K, 2>(ctx, p);
 			return;
 		}
 	}
-	if (low_bits >= 11 - K) {
+	if constexpr (K >= 9) {
+		/* 512- and 1024-point column tiles (n = 2^17, 2^18): 8 columns,
+		 * 512 / 1024 threads */
+		run_cols_cl<INV, K, 3, 1>(ctx, p);
+	} else if (low_bits >= 11 - K) {
 		run_cols_cl<INV, K, 11 - K, 1>(ctx, p);
 	} else if (K == 3 && low_bits == 7) {
 		run_cols_cl<INV, 3, 7, 1>(ctx, p);
@@ -679,6 +685,8 @@ static void run_cols_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
 	case 6: run_cols<INV, 6>(ctx, p); break;
 	case 7: run_cols<INV, 7>(ctx, p); break;
 	case 8: run_cols<INV, 8>(ctx, p); break;
+	case 9: run_cols<INV, 9>(ctx, p); break;
+	case 10: run_cols<INV, 10>(ctx, p); break;
 	default: VK_DIE("internal: column pass of %u stages", k);
 	}
 }
@@ -692,7 +700,7 @@ static fast_plan plan_fast(unsigned log2n) {
 	fast_plan pl = { 0, 0, 0 };
 	if (log2n <= 8) {
 		pl.krow = log2n;
-	} else if (log2n <= 16) {
+	} else if (log2n <= 18) {
 		pl.krow = log2n - 8 >= 3 ? 8 : log2n - 3;
 		pl.kcol = log2n - pl.krow;
 	} else {
