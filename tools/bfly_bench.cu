@@ -214,6 +214,72 @@ struct only_dfma { static const char *name() { return "2x DFMA only (fp64 pipe r
 		x = (u64) __double_as_longlong(a); y = (u64) __double_as_longlong(b);
 	} };
 
+/* ---- V12: csub through the borrow of a 64-bit subtraction (PTX carry chain) ---- */
+__device__ __forceinline__ u64 csub_borrow(u64 x, u64 m) {
+	const u32 xl = (u32) x, xh = (u32) (x >> 32), ml = (u32) m, mh = (u32) (m >> 32);
+	u32 tl, th, b;
+	asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;"
+			: "=r"(tl), "=r"(th), "=r"(b) : "r"(xl), "r"(xh), "r"(ml), "r"(mh));
+	const u32 rl = b ? xl : tl, rh = b ? xh : th;
+	return ((u64) rh << 32) | rl;
+}
+struct ct_v12 { static const char *name() { return "CT v12 harvey, csub via borrow chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 t = y * c.w - __umul64hi(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+struct ct_v13 { static const char *name() { return "CT v13 = v12 with twiddle LDS.128 per butterfly"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const ulonglong2 w = sm_tw[(threadIdx.x + (unsigned) x) & 255];
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 t = y * w.x - __umul64hi(y, w.y) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+struct gs_v12 { static const char *name() { return "GS v12 csub via borrow chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = csub_borrow(s, c.twoq);
+		y = d * c.w - __umul64hi(d, c.wp) * c.q;
+	} };
+
+/* ---- V14: v12 + mulhi as an explicit mad/madc carry chain ---- */
+__device__ __forceinline__ u64 mulhi_chain(u64 a, u64 b) {
+	const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+	u32 r0, r1, r2;
+	asm("{\n\t"
+		"mul.hi.u32 %0, %3, %5;\n\t"
+		"mad.lo.cc.u32 %0, %3, %6, %0;\n\t"
+		"madc.hi.u32 %1, %3, %6, 0;\n\t"
+		"mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+		"madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+		"addc.u32 %2, 0, 0;\n\t"
+		"mad.lo.cc.u32 %1, %4, %6, %1;\n\t"
+		"madc.hi.u32 %2, %4, %6, %2;\n\t"
+		"}" : "=&r"(r0), "=&r"(r1), "=&r"(r2) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+	return ((u64) r2 << 32) | r1;
+}
+struct ct_v14 { static const char *name() { return "CT v14 = v12 + mulhi mad/madc chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 t = y * c.w - mulhi_chain(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+/* ---- V15: v12 with the two low products fused: t = lo64(y*w - hi*q) by hand ---- */
+struct ct_v15 { static const char *name() { return "CT v15 = v12, low products with mad.wide + mad.lo"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 hi = __umul64hi(y, c.wp);
+		const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) c.w, w1 = (u32) (c.w >> 32);
+		const u32 h0 = (u32) hi, h1 = (u32) (hi >> 32), q0 = (u32) c.q, q1 = (u32) (c.q >> 32);
+		u64 a = (u64) y0 * w0;                       /* mul.wide */
+		u32 ah = (u32) (a >> 32) + y0 * w1 + y1 * w0;  /* 2 mad.lo */
+		u64 b = (u64) h0 * q0;
+		u32 bh = (u32) (b >> 32) + h0 * q1 + h1 * q0;
+		const u64 t = (((u64) ah << 32) | (u32) a) - (((u64) bh << 32) | (u32) b);
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -293,7 +359,7 @@ int main() {
 		run<ct_v0>(sms, c);
 	}
 	g_threads = 1024;
-	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v10>(sms, c); run<ct_v11>(sms, c); run<only_dfma>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v13>(sms, c); run<ct_v14>(sms, c); run<ct_v15>(sms, c); run<gs_v12>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);
