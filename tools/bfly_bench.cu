@@ -280,6 +280,32 @@ struct ct_v15 { static const char *name() { return "CT v15 = v12, low products w
 		x = xr + t; y = xr - t + c.twoq;
 	} };
 
+/* ---- V16: v12 with t = y*w + hi*(-q): no negation of the second product ---- */
+struct ct_v16 { static const char *name() { return "CT v16 = v12, t = y*w + hi*(2^64-q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 t = y * c.w + __umul64hi(y, c.wp) * nq;
+		x = xr + t; y = xr - t + c.twoq;
+	} };
+/* ---- V17: v16 + x' folded into the multiply-accumulate chain ---- */
+struct ct_v17 { static const char *name() { return "CT v17 = v16, x' = (xr + y*w) + hi*nq, y' = 2xr+2q-x'"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, c.twoq);
+		const u64 hi = __umul64hi(y, c.wp);
+		const u64 xn = hi * nq + (y * c.w + xr);
+		y = (xr + xr + c.twoq) - xn;
+		x = xn;
+	} };
+struct gs_v16 { static const char *name() { return "GS v16 = v12, t = d*w + hi*(2^64-q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 nq = 0 - c.q;
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = csub_borrow(s, c.twoq);
+		y = d * c.w + __umul64hi(d, c.wp) * nq;
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -359,7 +385,7 @@ int main() {
 		run<ct_v0>(sms, c);
 	}
 	g_threads = 1024;
-	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v13>(sms, c); run<ct_v14>(sms, c); run<ct_v15>(sms, c); run<gs_v12>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v14>(sms, c); run<ct_v16>(sms, c); run<ct_v17>(sms, c); run<gs_v12>(sms, c); run<gs_v16>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);

@@ -15,12 +15,35 @@
 
 typedef unsigned long long u64;
 
+/* High 64 bits of a 64x64 product as an explicit mad/madc carry chain.  Same
+ * value as __umul64hi; ptxas schedules this form with fewer carry fix-ups
+ * (tools/bfly_bench.cu v14: +2.7 % butterfly rate over mul.hi.u64). */
+__device__ __forceinline__ u64 mulhi64(u64 a, u64 b) {
+	const unsigned a0 = (unsigned) a, a1 = (unsigned) (a >> 32);
+	const unsigned b0 = (unsigned) b, b1 = (unsigned) (b >> 32);
+	unsigned r1, r2;
+	asm("{\n\t"
+	    ".reg .u32 r0;\n\t"
+	    "mul.hi.u32 r0, %2, %4;\n\t"           /* word 1 so far: hi(a0*b0) */
+	    "mad.lo.cc.u32 r0, %2, %5, r0;\n\t"    /* + lo(a0*b1) */
+	    "madc.hi.u32 %0, %2, %5, 0;\n\t"       /* word 2: hi(a0*b1) + carry */
+	    "mad.lo.cc.u32 r0, %3, %4, r0;\n\t"    /* word 1 += lo(a1*b0) */
+	    "madc.hi.cc.u32 %0, %3, %4, %0;\n\t"   /* word 2 += hi(a1*b0) + carry */
+	    "addc.u32 %1, 0, 0;\n\t"               /* word 3: carry */
+	    "mad.lo.cc.u32 %0, %3, %5, %0;\n\t"    /* word 2 += lo(a1*b1) */
+	    "madc.hi.u32 %1, %3, %5, %1;\n\t"      /* word 3 += hi(a1*b1) + carry */
+	    "}"
+	    : "=&r"(r1), "=&r"(r2)
+	    : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+	return ((u64) r2 << 32) | r1;
+}
+
 /* ---- Shoup multiplication by a fixed factor --------------------------------
  * w < q, wp = floor(w * 2^64 / q).  For ANY 64-bit y the lazy result is
  * y*w mod q + {0,q}, i.e. in [0,2q) (reference: nttfwdbutterfly.comp:44-48,
  * elemmulconst.comp:42-46, which then subtract q once). Needs q < 2^63. */
 __device__ __forceinline__ u64 shoup_lazy(u64 y, u64 w, u64 wp, u64 q) {
-	return y * w - __umul64hi(y, wp) * q;
+	return y * w - mulhi64(y, wp) * q;
 }
 
 __device__ __forceinline__ u64 shoup_canon(u64 y, u64 w, u64 wp, u64 q) {
