@@ -249,26 +249,29 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
  * passes stay lazy ([0,4q) forward, [0,2q) inverse) in the result vector.
  * ====================================================================================== */
 #define FAST_THREADS 256
-/* tuning knobs (tools/build_variant.sh): tiles per thread and occupancy targets */
-/* NP = 2 (two tiles per thread sharing each twiddle fetch) measured within 2 %
- * of NP = 1 on B200 (lower occupancy cancels the saved LDS): default 1 */
+/* Tuning knobs: tiles per thread (NP) and occupancy targets.
+ * Measured on B200 (tools/build_variant.sh + tools/bench_variants.sh, n = 2^16
+ * x 512): the row pass is fastest with one tile per thread and 6 CTAs per SM
+ * (40 registers, a few spill slots); the column pass with two adjacent columns
+ * per thread (128-bit accesses, each twiddle fetch feeding two butterflies) and
+ * 4 CTAs per SM (64 registers). */
 #ifndef ROWS_NP
 #define ROWS_NP 1
 #endif
 #ifndef COLS_NP
-#define COLS_NP 1
+#define COLS_NP 2
 #endif
 #ifndef ROWS_MIN_CTAS_NP1
-#define ROWS_MIN_CTAS_NP1 5
+#define ROWS_MIN_CTAS_NP1 6
 #endif
 #ifndef ROWS_MIN_CTAS_NP2
-#define ROWS_MIN_CTAS_NP2 3
+#define ROWS_MIN_CTAS_NP2 4
 #endif
 #ifndef COLS_MIN_THREADS_NP1
 #define COLS_MIN_THREADS_NP1 1280
 #endif
 #ifndef COLS_MIN_THREADS_NP2
-#define COLS_MIN_THREADS_NP2 768
+#define COLS_MIN_THREADS_NP2 1024
 #endif
 
 struct fast_pass {
