@@ -509,9 +509,11 @@ ntt_cols_kernel(const fast_pass p) {
 	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
 			C::threads);
 	const bool fold = INV && s0 == 0;
-	/* the forward transform always ends in a row pass; the inverse ends here
-	 * when this pass holds stage 0 */
-	const bool canon = INV && s0 == 0;
+	/* this pass stores canonical residues when it holds the last stage: stage
+	 * 0 for the inverse; the forward transform normally ends in a row pass
+	 * (a one-CTA-per-polynomial single-launch variant, K = log2 n, was
+	 * measured no faster than the two-pass split even for one polynomial) */
+	const bool canon = INV ? s0 == 0 : s0 + K == L;
 	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
 	if (fold) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
@@ -560,6 +562,9 @@ ntt_cols_kernel(const fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			u64 w = x[pp][e];
 			if (canon) {
+				if (!INV) {
+					w = csub(w, twoq);
+				}
 				w = csub(w, q);
 			}
 			((u64 *) &v)[pp] = w;
@@ -623,7 +628,7 @@ template <bool INV, int K, int CL, int NP>
 static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	using C = col_cfg<K, CL, NP>;
 	const unsigned low_bits = p.log2n - p.s0 - K;
-	VK_REQUIRE(low_bits >= (unsigned) CL,
+	VK_REQUIRE((int) low_bits >= CL,
 			"internal: column pass narrower than its CTA");
 	const u64 blocks = (p.polys << p.s0) << (low_bits - CL);
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
