@@ -307,6 +307,15 @@ def run_native_arm(args):
         barrier()
         return max_over_ranks(ms), ctx.launch_count - l0
 
+    # bring the GPU out of its idle clocks before anything is timed: an idle
+    # B200 sits at 120 MHz and needs tens of milliseconds of load to reach its
+    # boost clock; W steps of 0.8 ms are too short for that
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.25:
+        for _ in range(20):
+            step_resident()
+        ctx.sync()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

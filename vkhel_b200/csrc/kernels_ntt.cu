@@ -273,6 +273,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef COLS_MIN_THREADS_NP2
 #define COLS_MIN_THREADS_NP2 1024
 #endif
+#ifndef ROWS_ROUNDS_PER_CTA
+#define ROWS_ROUNDS_PER_CTA 2
+#endif
 
 struct fast_pass {
 	const u64 *src;
@@ -509,11 +512,11 @@ ntt_cols_kernel(const fast_pass p) {
 	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
 			C::threads);
 	const bool fold = INV && s0 == 0;
-	/* this pass stores canonical residues when it holds the last stage: stage
-	 * 0 for the inverse; the forward transform normally ends in a row pass
-	 * (a one-CTA-per-polynomial single-launch variant, K = log2 n, was
-	 * measured no faster than the two-pass split even for one polynomial) */
-	const bool canon = INV ? s0 == 0 : s0 + K == L;
+	/* the forward transform always ends in a row pass; the inverse ends here
+	 * when this pass holds stage 0.  (A one-CTA-per-polynomial single-launch
+	 * variant of this kernel, K = log2 n, was measured no faster than the
+	 * two-pass split even for a single polynomial.) */
+	const bool canon = INV && s0 == 0;
 	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
 	if (fold) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
@@ -562,9 +565,6 @@ ntt_cols_kernel(const fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			u64 w = x[pp][e];
 			if (canon) {
-				if (!INV) {
-					w = csub(w, twoq);
-				}
 				w = csub(w, q);
 			}
 			((u64 *) &v)[pp] = w;
@@ -587,7 +587,7 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		hgroup_log2++;
 	}
 	/* two rounds of items per CTA amortise the twiddle staging */
-	u64 bchunk = (2 * slots) >> hgroup_log2;
+	u64 bchunk = (ROWS_ROUNDS_PER_CTA * slots) >> hgroup_log2;
 	if (bchunk < (u64) NP) {
 		bchunk = NP;
 	}
