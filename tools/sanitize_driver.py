@@ -1,0 +1,68 @@
+#!/usr/bin/env python3
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck):
+every kernel family once, checked against the oracle.
+
+    compute-sanitizer --tool racecheck python tools/sanitize_driver.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402
+import vkhel_b200 as vk  # noqa: E402
+from vkhel_b200 import params  # noqa: E402
+
+
+def main():
+    rng = np.random.default_rng(0)
+    ctx = vk.Context(0)
+    # (log2n, limbs, batch): row-only, column+row (several tile shapes),
+    # 512-point column tiles, leading generic pass, generic tiny sizes
+    shapes = [(2, 1, 3), (5, 1, 9), (8, 2, 3), (10, 1, 5), (12, 3, 2),
+              (14, 1, 2), (16, 2, 1), (17, 1, 1)]
+    for log2n, limbs, batch in shapes:
+        n = 1 << log2n
+        primes = params.ntt_primes(limbs)
+        tabs = [vk.NttTables(n, q, params.find_psi(n, q)) for q in primes]
+        oras = [oracle.Tables(n, q, t.w) for q, t in zip(primes, tabs)]
+        polys = limbs * batch
+        x = np.concatenate([rng.integers(0, primes[p % limbs], n, dtype=np.uint64)
+                            for p in range(polys)])
+        a, b = ctx.from_host(x), ctx.vector(x.size)
+        ctx.forward_transform_rns(a, b, tabs, batch)
+        assert np.array_equal(b.to_host(), oracle.forward_batch(x, oras, threads=4))
+        ctx.inverse_transform_rns(b, b, tabs, batch)
+        assert np.array_equal(b.to_host(), x)
+        ctx.elemmul_rns(a, b, b, primes, n, batch) if n >= 2 else None
+        a.destroy(), b.destroy()
+        for t in tabs:
+            t.destroy()
+    # strict path (63-bit modulus) and the legacy entry points
+    n, q = 256, params.Q63_STRICT
+    t = vk.NttTables(n, q, params.find_psi(n, q))
+    x = rng.integers(0, q, n + 5, dtype=np.uint64)
+    v = ctx.from_host(x)
+    ctx.forward_transform(v, v, t)
+    ctx.inverse_transform(v, v, t)
+    v.to_host()
+    q = 769
+    a = ctx.from_host(rng.integers(0, 1 << 62, 1001, dtype=np.uint64))
+    c = ctx.vector(1001)
+    ctx.elemmul(a, a, c, q)
+    ctx.elemfma(a, a, c, 5, q)
+    ctx.elemgtadd(a, c, 7, 9)
+    ctx.elemgtsub(a, c, 7, 9, q)
+    ctx.elemmod(a, c, 2, q)
+    ctx.elemmod(a, c, 3, q)
+    c.to_host()
+    for vec in (v, a, c):
+        vec.destroy()
+    t.destroy()
+    ctx.destroy()
+    print("sanitize driver ok")
+
+
+if __name__ == "__main__":
+    main()

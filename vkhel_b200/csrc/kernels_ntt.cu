@@ -387,9 +387,23 @@ ntt_rows_kernel(const fast_pass p) {
 			const u64 poly = (b0 + bl) * p.limbs + limb;
 			off[pp] = (poly << L) + ((u64) (H0 + h) << K);
 			const u64 *sp = p.src + off[pp] + tb_first;
+			if (G::eoff(first, 1) == 1) {
+				/* registers (e, e+1) are adjacent coefficients (the layout of
+				 * the deepest round): 128-bit loads */
 #pragma unroll
-			for (int e = 0; e < 8; e++) {
-				x[pp][e] = active[pp] ? sp[G::eoff(first, e)] : 0;
+				for (int e = 0; e < 8; e += 2) {
+					ulonglong2 v = make_ulonglong2(0, 0);
+					if (active[pp]) {
+						v = *(const ulonglong2 *) (sp + G::eoff(first, e));
+					}
+					x[pp][e] = v.x;
+					x[pp][e + 1] = v.y;
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					x[pp][e] = active[pp] ? sp[G::eoff(first, e)] : 0;
+				}
 			}
 		}
 
@@ -431,14 +445,25 @@ ntt_rows_kernel(const fast_pass p) {
 				u64 *dp = p.dst + off[pp] + tb_last;
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
-					u64 v = x[pp][e];
 					if (canon) {
 						if (!INV) {
-							v = csub(v, twoq);
+							x[pp][e] = csub(x[pp][e], twoq);
 						}
-						v = csub(v, q);
+						x[pp][e] = csub(x[pp][e], q);
 					}
-					dp[G::eoff(last, e)] = v;
+				}
+				if (G::eoff(last, 1) == 1) {
+					/* adjacent coefficients in (e, e+1): 128-bit stores */
+#pragma unroll
+					for (int e = 0; e < 8; e += 2) {
+						*(ulonglong2 *) (dp + G::eoff(last, e)) =
+							make_ulonglong2(x[pp][e], x[pp][e + 1]);
+					}
+				} else {
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						dp[G::eoff(last, e)] = x[pp][e];
+					}
 				}
 			}
 		}
