@@ -276,6 +276,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef ROWS_ROUNDS_PER_CTA
 #define ROWS_ROUNDS_PER_CTA 2
 #endif
+#ifndef ROWS_PREFETCH
+#define ROWS_PREFETCH 1
+#endif
 
 struct fast_pass {
 	const u64 *src;
@@ -296,17 +299,60 @@ __host__ __device__ constexpr int xpad(int i) {
 	return i + ((i >> 5) << 2);
 }
 
-/* stage the twiddle subtrees rooted at nodes 2^s0 + H0 .. + hgroup - 1 */
+/* ---- twiddle staging by TMA bulk copies --------------------------------------------
+ * The twiddle subtree of a tile root is one contiguous run per level in the
+ * bit-reversed table (2^u pairs of 16 bytes at level u), so staging it is K
+ * one-dimensional bulk copies (cp.async.bulk, SASS UBLKCP) issued by a single
+ * thread and tracked by an mbarrier; the other threads go straight to their
+ * coefficient loads and only wait on the barrier before the first butterfly. */
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+	const unsigned addr = (unsigned) __cvta_generic_to_shared(bar);
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(addr), "r"(count));
+	/* make the initialised barrier visible to the async (TMA) proxy */
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, unsigned bytes) {
+	const unsigned addr = (unsigned) __cvta_generic_to_shared(bar);
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+			:: "r"(addr), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+	const unsigned addr = (unsigned) __cvta_generic_to_shared(bar);
+	asm volatile(
+		"{\n\t"
+		".reg .pred done;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
+		"@!done bra WAIT_%=;\n\t"
+		"}" :: "r"(addr), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem,
+		unsigned bytes, u64 *bar) {
+	const unsigned dst = (unsigned) __cvta_generic_to_shared(smem);
+	const unsigned mb = (unsigned) __cvta_generic_to_shared(bar);
+	asm volatile(
+		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+		"[%0], [%1], %2, [%3];"
+		:: "r"(dst), "l"(gmem), "r"(bytes), "r"(mb) : "memory");
+}
+
+/* issue (one thread) the copies of the subtrees rooted at nodes
+ * 2^s0 + H0 .. + hgroup - 1 into sm_tw[h << K | node] */
 template <int K>
-__device__ __forceinline__ void stage_twiddles(ulonglong2 *sm_tw,
+__device__ __forceinline__ void stage_twiddles_tma(ulonglong2 *sm_tw,
 		const ulonglong2 *tw_g, unsigned s0, u64 H0, unsigned hgroup,
-		unsigned threads) {
-	for (unsigned v = threadIdx.x; v < (hgroup << K); v += threads) {
-		const unsigned h = v >> K, node = v & ((1u << K) - 1);
-		if (node) {
-			const unsigned u = 31 - __clz(node);
-			const u64 root = ((u64) 1 << s0) + H0 + h;
-			sm_tw[v] = tw_g[(root << u) + (node - (1u << u))];
+		u64 *bar) {
+	/* every level u moves 2^u pairs: (2^K - 1) pairs per root */
+	mbar_expect_tx(bar, hgroup * ((1u << K) - 1) * (unsigned) sizeof(ulonglong2));
+	for (unsigned h = 0; h < hgroup; h++) {
+		const u64 root = ((u64) 1 << s0) + H0 + h;
+#pragma unroll
+		for (unsigned u = 0; u < (unsigned) K; u++) {
+			bulk_g2s(sm_tw + ((size_t) h << K) + (1u << u), tw_g + (root << u),
+					(unsigned) sizeof(ulonglong2) << u, bar);
 		}
 	}
 }
@@ -350,9 +396,16 @@ ntt_rows_kernel(const fast_pass p) {
 
 	const limb_desc &d = p.descs[limb];
 	const u64 q = d.q, twoq = 2 * q;
-	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H0, hgroup,
-			FAST_THREADS);
+	__shared__ __align__(8) u64 tw_bar;
+	if (threadIdx.x == 0) {
+		mbar_init(&tw_bar, 1);
+	}
 	__syncthreads();
+	if (threadIdx.x == 0) {
+		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H0,
+				hgroup, &tw_bar);
+	}
+	bool tw_ready = false;
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int t = lane & (C::group - 1);                 /* thread within group */
@@ -380,6 +433,22 @@ ntt_rows_kernel(const fast_pass p) {
 		bool active[NP];
 		u64 off[NP];
 		u64 x[NP][8];
+#if ROWS_PREFETCH
+		/* pull the tile this slot takes in the next iteration towards the
+		 * SM while this one is being computed: one 128-byte line per lane
+		 * of the group, no registers held */
+		{
+			const unsigned nidx = idx + C::groups_per_cta;
+			const unsigned nh = nidx & (hgroup - 1);
+			const unsigned nbl = (nidx >> p.hgroup_log2) * NP;
+			if (nidx < nitems && nbl < nb && (t << 4) < (1 << K)) {
+				const u64 npoly = (b0 + nbl) * p.limbs + limb;
+				const u64 *np_ = p.src + (npoly << L) + ((u64) (H0 + nh) << K)
+					+ (t << 4);
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(np_));
+			}
+		}
+#endif
 #pragma unroll
 		for (int pp = 0; pp < NP; pp++) {
 			const unsigned bl = bg * NP + pp;
@@ -407,6 +476,10 @@ ntt_rows_kernel(const fast_pass p) {
 			}
 		}
 
+		if (!tw_ready) {
+			mbar_wait(&tw_bar, 0);   /* twiddles have landed */
+			tw_ready = true;
+		}
 #pragma unroll
 		for (int rr = 0; rr < G::rounds; rr++) {
 			const int r = INV ? G::rounds - 1 - rr : rr;
@@ -534,8 +607,15 @@ ntt_cols_kernel(const fast_pass p) {
 			}
 		}
 	}
-	stage_twiddles<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
-			C::threads);
+	__shared__ __align__(8) u64 tw_bar;
+	if (threadIdx.x == 0) {
+		mbar_init(&tw_bar, 1);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
+				&tw_bar);
+	}
 	const bool fold = INV && s0 == 0;
 	/* the forward transform always ends in a row pass; the inverse ends here
 	 * when this pass holds stage 0.  (A one-CTA-per-polynomial single-launch
@@ -547,7 +627,7 @@ ntt_cols_kernel(const fast_pass p) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
 		fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
 	}
-	__syncthreads();   /* twiddles staged */
+	mbar_wait(&tw_bar, 0);   /* twiddles have landed */
 
 #pragma unroll
 	for (int rr = 0; rr < G::rounds; rr++) {
