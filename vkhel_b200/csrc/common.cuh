@@ -44,7 +44,10 @@ struct limb_desc {
 	u64 q;
 	u64 inv_n, inv_n_shoup;       /* n^-1 and its Shoup companion */
 	u64 inv_w1n, inv_w1n_shoup;   /* inv_root[1] * n^-1: last inverse stage */
-	u64 pad_[2];
+	/* a*b mod q for canonical a, b (fused point-wise product): divisor
+	 * q << mm_s and its Moller-Granlund reciprocal, see struct modulus */
+	u64 mm_d, mm_v;
+	unsigned mm_s, pad_[3];
 };
 
 /* device.cu */
@@ -84,5 +87,11 @@ void launch_elemmodbytwo(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, uint64_t q_max);
+/* inverse transform of the point-wise product src * src2 (both canonical, in
+ * the transform domain); returns false when the fused kernel does not apply
+ * and the caller has to multiply separately */
+bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
+		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max);
 
 #endif

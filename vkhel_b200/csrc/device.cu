@@ -310,6 +310,10 @@ static void fill_desc(const struct vkhel_ntt_tables *ntt, limb_desc *desc,
 		desc->inv_w1n_shoup = nt_compute_barrett_factor(desc->inv_w1n,
 				ntt->q, 64);
 	}
+	const struct modulus m = make_modulus(ntt->q);
+	desc->mm_d = m.d;
+	desc->mm_v = m.v;
+	desc->mm_s = m.s;
 }
 
 static void *ensure_mirror(struct vkhel_ctx *ctx,

@@ -282,6 +282,7 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 
 struct fast_pass {
 	const u64 *src;
+	const u64 *src2;      /* row pass, MUL: second factor of the point-wise product */
 	u64 *dst;
 	const limb_desc *descs;
 	unsigned limbs;
@@ -369,7 +370,7 @@ struct row_cfg {
 /* Row pass.  CTA = (batch chunk, limb, H group): `bchunk` batch entries of
  * 2^hgroup_log2 consecutive tiles sharing one staged twiddle set.  A warp-group
  * of 2^(K-3) lanes carries NP batch entries of one tile position at a time. */
-template <bool INV, int K, int NP>
+template <bool INV, int K, int NP, bool MUL>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const fast_pass p) {
@@ -472,6 +473,23 @@ ntt_rows_kernel(const fast_pass p) {
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					x[pp][e] = active[pp] ? sp[G::eoff(first, e)] : 0;
+				}
+			}
+			if (MUL) {
+				/* fused point-wise product (the reference's elemmul between
+				 * the forward and the inverse transform, src/vector.c:388-427):
+				 * both factors are canonical transform outputs */
+				modulus m;
+				m.q = q;
+				m.d = d.mm_d;
+				m.v = d.mm_v;
+				m.s = d.mm_s;
+				m.mu = 0;
+				const u64 *sp2 = p.src2 + off[pp] + tb_first;
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					const u64 y = active[pp] ? sp2[G::eoff(first, e)] : 0;
+					x[pp][e] = mulmod(x[pp][e], y, m);
 				}
 			}
 		}
@@ -678,7 +696,7 @@ ntt_cols_kernel(const fast_pass p) {
 	}
 }
 
-template <bool INV, int K, int NP>
+template <bool INV, int K, int NP, bool MUL>
 static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	using C = row_cfg<K>;
 	const u64 batch = p.polys / p.limbs;
@@ -708,10 +726,10 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
 	if (smem > 48 * 1024) {
 		/* per device, and cheap: set it on every such launch */
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP>,
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP, MUL>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	ntt_rows_kernel<INV, K, NP><<<(unsigned) blocks, FAST_THREADS, smem,
+	ntt_rows_kernel<INV, K, NP, MUL><<<(unsigned) blocks, FAST_THREADS, smem,
 		ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	ctx->dev.launches++;
@@ -719,14 +737,20 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 
 template <bool INV, int K>
 static void run_rows(struct vkhel_ctx *ctx, const fast_pass &p) {
-	/* two batch entries per thread when there are two to pair up */
-	if constexpr (ROWS_NP == 2) {
-		if (p.polys / p.limbs >= 2) {
-			run_rows_np<INV, K, 2>(ctx, p);
+	if constexpr (INV) {
+		if (p.src2) {
+			run_rows_np<INV, K, 1, true>(ctx, p);
 			return;
 		}
 	}
-	run_rows_np<INV, K, 1>(ctx, p);
+	/* two batch entries per thread when there are two to pair up */
+	if constexpr (ROWS_NP == 2) {
+		if (p.polys / p.limbs >= 2) {
+			run_rows_np<INV, K, 2, false>(ctx, p);
+			return;
+		}
+	}
+	run_rows_np<INV, K, 1, false>(ctx, p);
 }
 
 template <bool INV, int K, int CL, int NP>
@@ -827,9 +851,10 @@ static fast_plan plan_fast(unsigned log2n) {
 template <bool INV>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
-		unsigned log2n) {
+		unsigned log2n, const u64 *src2 = NULL) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
+	p.src2 = NULL;
 	p.descs = descs;
 	p.limbs = (unsigned) limbs;
 	p.log2n = log2n;
@@ -867,9 +892,11 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		run_rows_k<false>(ctx, p, pl.krow);
 	} else {
 		p.src = src;
+		p.src2 = src2;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
 		run_rows_k<true>(ctx, p, pl.krow);
+		p.src2 = NULL;
 		if (pl.kcol) {
 			p.src = dst;
 			p.s0 = pl.lead;
@@ -906,4 +933,14 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		if (strict) run_generic<false, true>(ctx, src, dst, descs, limbs, polys, log2n);
 		else run_generic<false, false>(ctx, src, dst, descs, limbs, polys, log2n);
 	}
+}
+
+bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
+		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max) {
+	if (q_max >= (1ull << 62) || log2n < 3 || getenv("VKHEL_FORCE_GENERIC")) {
+		return false;   /* generic path: no fused product */
+	}
+	run_fast<true>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+	return true;
 }

@@ -444,8 +444,8 @@ extern "C" void vkhel_vector_polymul_rns(
 	if (batch == 0) {
 		return;
 	}
-	/* unfused sequence of the reference API: NTT(a) -> result,
-	 * NTT(b) -> scratch, product, inverse */
+	/* the reference API sequence NTT(a) -> result, NTT(b) -> scratch,
+	 * product, inverse -- with the product folded into the inverse */
 	u64 *tmp = (u64 *) device_scratch(ctx, total * sizeof(u64));
 	uint64_t mods[64];
 	for (uint64_t l = 0; l < limbs; l++) {
@@ -456,8 +456,13 @@ extern "C" void vkhel_vector_polymul_rns(
 			limbs * batch, log2n, q_max);
 	launch_ntt(ctx, false, dev_u64(b), tmp, descs, limbs, limbs * batch,
 			log2n, q_max);
-	launch_elemmul_rns(ctx, dev_u64(result), tmp, dev_u64(result), mods,
-			limbs, n, batch);
-	launch_ntt(ctx, true, dev_u64(result), dev_u64(result), descs, limbs,
-			limbs * batch, log2n, q_max);
+	/* point-wise product fused into the first pass of the inverse transform
+	 * where the fast path applies; otherwise the separate element-wise kernel */
+	if (!launch_ntt_inverse_of_product(ctx, dev_u64(result), tmp,
+				dev_u64(result), descs, limbs, limbs * batch, log2n, q_max)) {
+		launch_elemmul_rns(ctx, dev_u64(result), tmp, dev_u64(result), mods,
+				limbs, n, batch);
+		launch_ntt(ctx, true, dev_u64(result), dev_u64(result), descs, limbs,
+				limbs * batch, log2n, q_max);
+	}
 }
