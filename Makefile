@@ -41,8 +41,9 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 	$(BIN_DIR)/ref_example $(BIN_DIR)/ref_test_vector \
 	$(BIN_DIR)/ref_test_ntt $(BIN_DIR)/ref_test_numbers,)
 
-.PHONY: all libs oracle refbins clean check check-host
-all: libs oracle refbins
+.PHONY: all libs oracle refbins examples clean check check-host
+all: libs oracle refbins examples
+examples: $(BIN_DIR)/multi_gpu
 libs: $(SHARED) $(STATIC)
 refbins: $(REF_BINS)
 
@@ -73,6 +74,11 @@ $(BIN_DIR)/ref_example: $(REF)/examples/example.c $(SHARED)
 $(BIN_DIR)/ref_test_%: $(REF)/test/%.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# this repository's own example: limb-sharded transform over every visible GPU
+$(BIN_DIR)/multi_gpu: examples/multi_gpu.c $(STATIC)
+	@mkdir -p $(BIN_DIR)
+	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 
 oracle:
 	$(MAKE) -C oracle REF=$(REF)

@@ -44,6 +44,14 @@ void vkhel_vector_upload(struct vkhel_vector *, const uint64_t *src,
 void vkhel_vector_download(const struct vkhel_vector *, uint64_t *dst,
 		uint64_t offset, uint64_t count);
 
+/* copy `count` elements between vectors that may live in different contexts
+ * (different GPUs: the copy goes over NVLink peer-to-peer).  Ordered after the
+ * work enqueued so far on the source context and before later work on the
+ * destination context.  This is the "gather the shards on request" step of a
+ * multi-GPU run; the transforms themselves need no exchange. */
+void vkhel_vector_copy_peer(struct vkhel_vector *dst, uint64_t dst_offset,
+		const struct vkhel_vector *src, uint64_t src_offset, uint64_t count);
+
 /* ---- batched / RNS transforms --------------------------------------------
  * Same arithmetic per polynomial as vkhel_vector_forward_transform /
  * vkhel_vector_inverse_transform (reference src/vector.c:513-657); exactly

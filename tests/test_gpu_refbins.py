@@ -31,3 +31,17 @@ def test_reference_program(name):
             assert "%s passed" % t in res.stdout
     if name == "ref_example":
         assert res.stdout.count("{4, 0, 0, 4, }") == 2
+
+
+def test_multi_gpu_example():
+    """examples/multi_gpu.c: limb-sharded transform over every visible GPU
+    (host thread + context per GPU), gathered with vkhel_vector_copy_peer and
+    compared with the single-GPU result; degenerates gracefully to 1 GPU"""
+    path = os.path.join(BIN, "multi_gpu")
+    if not os.path.exists(path):
+        pytest.fail("%s missing: run `make`" % path)
+    for args in (["12", "8", "4"], ["16", "5", "2"], ["4", "3", "7"]):
+        res = subprocess.run([path] + args, capture_output=True, text=True,
+                             timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert "== single-GPU result" in res.stdout

@@ -59,6 +59,7 @@ SIGNATURES = {
     "vkhel_vector_device_ptr": (_vp, [_vp]),
     "vkhel_vector_upload": (None, [_vp, _vp, _u64, _u64]),
     "vkhel_vector_download": (None, [_vp, _vp, _u64, _u64]),
+    "vkhel_vector_copy_peer": (None, [_vp, _u64, _vp, _u64, _u64]),
     "vkhel_vector_forward_transform_batch": (None, [_vp, _vp, _vp, _u64]),
     "vkhel_vector_inverse_transform_batch": (None, [_vp, _vp, _vp, _u64]),
     "vkhel_vector_forward_transform_rns": (None, [_vp, _vp,
@@ -194,6 +195,12 @@ class Vector:
             out = np.empty(0, np.uint64)
         lib().vkhel_vector_unmap(self.handle)
         return out
+
+    def copy_peer(self, src, dst_offset=0, src_offset=0, count=None):
+        """device -> device copy, possibly across GPUs (NVLink P2P)"""
+        count = src.length - src_offset if count is None else count
+        lib().vkhel_vector_copy_peer(self.handle, dst_offset, src.handle,
+                                     src_offset, count)
 
     def upload(self, pinned, offset=0, count=None, host_offset=0):
         """enqueue host -> device: pinned[host_offset:+count] -> self[offset:]"""

@@ -210,6 +210,50 @@ extern "C" void vkhel_vector_download(const struct vkhel_vector *cvec,
 	}
 }
 
+extern "C" void vkhel_vector_copy_peer(struct vkhel_vector *dst,
+		uint64_t dst_offset, const struct vkhel_vector *src,
+		uint64_t src_offset, uint64_t count) {
+	VK_REQUIRE(dst_offset + count <= dst->length
+			&& src_offset + count <= src->length, "copy_peer out of range");
+	if (!count) {
+		return;
+	}
+	struct vkhel_ctx *sctx = src->ctx, *dctx = dst->ctx;
+	/* source side: an event after everything enqueued on its stream */
+	enter(sctx);
+	const u64 *sp = dev_u64(src) + src_offset;
+	cudaEvent_t ready = (cudaEvent_t) sctx->dev.ev_scratch;
+	CUDA_CHECK(cudaEventRecord(ready, ctx_stream(sctx)));
+	/* destination side: wait for it, then copy on the destination stream */
+	enter(dctx);
+	u64 *dp = dev_u64(dst) + dst_offset;
+	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(dctx), ready, 0));
+	if (sctx->dev.device == dctx->dev.device) {
+		CUDA_CHECK(cudaMemcpyAsync(dp, sp, count * sizeof(u64),
+					cudaMemcpyDeviceToDevice, ctx_stream(dctx)));
+	} else {
+		/* direct NVLink path when the devices can address each other;
+		 * cudaMemcpyPeerAsync stages through the host otherwise */
+		int can = 0;
+		CUDA_CHECK(cudaDeviceCanAccessPeer(&can, dctx->dev.device,
+					sctx->dev.device));
+		if (can) {
+			cudaError_t err = cudaDeviceEnablePeerAccess(sctx->dev.device, 0);
+			if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) {
+				VK_DIE("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err));
+			}
+			(void) cudaGetLastError();
+		}
+		CUDA_CHECK(cudaMemcpyPeerAsync(dp, dctx->dev.device, sp,
+					sctx->dev.device, count * sizeof(u64), ctx_stream(dctx)));
+	}
+	/* the source must not be overwritten before the copy has read it */
+	cudaEvent_t done = (cudaEvent_t) dctx->dev.ev_scratch;
+	CUDA_CHECK(cudaEventRecord(done, ctx_stream(dctx)));
+	enter(sctx);
+	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(sctx), done, 0));
+}
+
 /* ---- debug tracing (reference: VKHEL_DEBUG blocks, e.g. vector.c:305-314) --- */
 #ifdef VKHEL_DEBUG
 #define DBG_VEC(label, v) do { printf("\t%s: ", label); \
