@@ -74,6 +74,17 @@ def main():
     print(json.dumps({"config": "polymul n=2^16 batch 128 (per-GPU share of configs[3])",
                       "ms": ms, "polymul_per_s": batch / ms * 1e3,
                       "api_bytes_GBps": 72 * n * batch / ms / 1e6}))
+    # element-wise kernels (HBM-bound): 2^27 elements, 24 or 16 bytes each
+    cfull = ctx.vector(total, zero=False)
+    for name, fn, nbytes in (
+            ("elemmul", lambda: ctx.elemmul(a, b, cfull, q), 24),
+            ("elemfma", lambda: ctx.elemfma(a, b, cfull, 12345, q), 24),
+            ("elemgtsub", lambda: ctx.elemgtsub(a, cfull, q // 2, 7, q), 16),
+            ("elemgtadd", lambda: ctx.elemgtadd(a, cfull, q // 2, 7), 16)):
+        ms = time_ms(ctx, timer, fn, 10)
+        print(json.dumps({"config": name + " 2^%d elements" % args.log2_total,
+                          "ms": ms, "GBps": nbytes * total / ms / 1e6}))
+    cfull.destroy()
     # legacy single-vector API, one transform per call (launch-bound regime)
     for log2n in (12, 16):
         n = 1 << log2n

@@ -26,23 +26,38 @@ struct modulus make_modulus(uint64_t q) {
 }
 
 /* ---- per-element operations ------------------------------------------------------ */
-struct op_mul { /* reference elemmul.comp:62-73 */
+/* (a mod q)(b mod q) mod q for arbitrary 64-bit a, b (reference
+ * elemmul.comp:62-73 reduces both operands first).  Here the full product is
+ * formed once: a*b = hi*2^64 + lo = (hi mod q)*2^64 + lo (mod q), and the
+ * two-word division needs hi < q -- true whenever the operands are canonical,
+ * so the extra reduction of hi sits behind a branch that canonical data never
+ * takes. */
+__device__ __forceinline__ u64 mulmod_any(u64 a, u64 b, const modulus &m) {
+	u64 hi = __umul64hi(a, b);
+	const u64 lo = a * b;
+	if (hi >= m.q) {
+		hi = reduce64(hi, m);
+	}
+	return reduce128(hi, lo, m);
+}
+
+struct op_mul {
 	modulus m;
 	__device__ __forceinline__ u64 operator()(u64 a, u64 b) const {
-		return mulmod(reduce64(a, m), reduce64(b, m), m);
+		return mulmod_any(a, b, m);
 	}
 };
 
 struct op_fma { /* contract of elemfma (shader defect Q2) */
 	modulus m;
-	u64 mult; /* already reduced */
+	u64 mult; /* reduced on the host: mult <= q - 1 */
 	__device__ __forceinline__ u64 operator()(u64 a, u64 b) const {
-		const u64 ar = reduce64(a, m);
-		const u64 br = reduce64(b, m);
-		/* ar*mult + br <= (q-1)^2 + (q-1) < q^2: high word stays below q */
-		const u64 lo = ar * mult;
-		const u64 sum = lo + br;
-		const u64 hi = __umul64hi(ar, mult) + (sum < lo);
+		/* a*mult + b for arbitrary a, b: the high word of a*mult is at most
+		 * mult - 1 <= q - 2, the carry of the addition raises it to at most
+		 * q - 1, so the two-word division applies directly */
+		const u64 lo = a * mult;
+		const u64 sum = lo + b;
+		const u64 hi = __umul64hi(a, mult) + (sum < lo);
 		return reduce128(hi, sum, m);
 	}
 };
@@ -244,14 +259,12 @@ elemmul_rns_kernel(const ulonglong2 *a,
 			b1 = b[j];
 		}
 		const modulus &m0 = mods.m[(i >> log2_vec_per_poly) % limbs];
-		out[i] = make_ulonglong2(
-				mulmod(reduce64(a0.x, m0), reduce64(b0.x, m0), m0),
-				mulmod(reduce64(a0.y, m0), reduce64(b0.y, m0), m0));
+		out[i] = make_ulonglong2(mulmod_any(a0.x, b0.x, m0),
+				mulmod_any(a0.y, b0.y, m0));
 		if (second) {
 			const modulus &m1 = mods.m[(j >> log2_vec_per_poly) % limbs];
-			out[j] = make_ulonglong2(
-					mulmod(reduce64(a1.x, m1), reduce64(b1.x, m1), m1),
-					mulmod(reduce64(a1.y, m1), reduce64(b1.y, m1), m1));
+			out[j] = make_ulonglong2(mulmod_any(a1.x, b1.x, m1),
+					mulmod_any(a1.y, b1.y, m1));
 		}
 	}
 }
