@@ -41,7 +41,7 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 	$(BIN_DIR)/ref_example $(BIN_DIR)/ref_test_vector \
 	$(BIN_DIR)/ref_test_ntt $(BIN_DIR)/ref_test_numbers,)
 
-.PHONY: all libs oracle refbins examples clean check check-host
+.PHONY: all libs oracle refbins examples tools clean check check-host
 all: libs oracle refbins examples
 examples: $(BIN_DIR)/multi_gpu
 libs: $(SHARED) $(STATIC)
@@ -79,6 +79,12 @@ $(BIN_DIR)/ref_test_%: $(REF)/test/%.c $(STATIC)
 $(BIN_DIR)/multi_gpu: examples/multi_gpu.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# micro-benchmarks behind the roofline denominators (profiles/*bench*.txt)
+tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench
+$(BIN_DIR)/%_bench: tools/%_bench.cu
+	@mkdir -p $(BIN_DIR)
+	$(NVCC) $(ARCH) -O3 -o $@ $<
 
 oracle:
 	$(MAKE) -C oracle REF=$(REF)
