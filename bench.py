@@ -43,9 +43,9 @@ METRIC = "64-bit NTTs/sec at n=2^16"
 BFLY_PEAK_G = 874.0          # lazy Harvey butterflies/s, best compiled form (v14)
 BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
 # DRAM bytes of one step (4 launches) from the ncu --set full capture
-# profiles/r01_ntt_v3_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
-NCU_TRAFFIC_BYTES_PER_STEP = int((268.594 + 229.818 + 301.891 + 216.038
-                                  + 301.996 + 217.487 + 268.612 + 217.899) * 1e6)
+# profiles/r01_ntt_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
+NCU_TRAFFIC_BYTES_PER_STEP = int((268.621 + 219.618 + 302.085 + 218.647
+                                  + 302.334 + 215.959 + 268.645 + 208.700) * 1e6)
 WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
             "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
             "step = forward + inverse of the whole batch")
@@ -380,7 +380,7 @@ def run_native_arm(args):
                 "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES_PER_STEP,
                 "traffic_source": "ncu --set full, profiles/"
-                                  "r01_ntt_v3_ncu_full.txt (two passes per "
+                                  "r01_ntt_ncu_full.txt (two passes per "
                                   "transform: ~2x the algorithmic bytes)",
                 "peak_source": peak_src,
                 "kernel": "whole step (forward + inverse NTT, all passes)",
