@@ -1,0 +1,203 @@
+"""GPU suite: edge cases of the C API beyond the reference's own tests --
+degenerate sizes, aliasing, tails, asynchronous ordering, several contexts,
+table lifetime, ragged RNS shapes."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import vkhel_b200 as vk
+from vkhel_b200 import params
+from conftest import u64, rand_mod, rand_u64
+from test_gpu_parity import TablePair, run_forward, run_inverse
+
+pytestmark = pytest.mark.gpu
+
+
+def test_degenerate_transform_sizes(ctx):
+    """n = 1: no butterfly stage.  The reference's forward leaves `result`
+    untouched and its inverse multiplies `result` (not operand) by 1 mod q
+    (src/vector.c:536-537, 633-639); n = 2: a single stage."""
+    q = params.P0
+    t1 = vk.NttTables(1, q, 1)
+    a = ctx.from_host(u64([5, 6, 7]))
+    b = ctx.from_host(u64([q + 3, 9, (1 << 64) - 1]))
+    ctx.forward_transform(a, b, t1)
+    assert b.to_host().tolist() == [q + 3, 9, (1 << 64) - 1]
+    ctx.inverse_transform(a, b, t1)
+    assert b.to_host().tolist() == [3, 9, ((1 << 64) - 1) % q]
+    a.destroy(), b.destroy(), t1.destroy()
+
+    tp = TablePair(2, q)
+    x = u64([q - 1, 12345])
+    assert np.array_equal(run_forward(ctx, x, tp), oracle.forward(x, tp.ora))
+    assert np.array_equal(run_inverse(ctx, x, tp), oracle.inverse(x, tp.ora))
+    tp.destroy()
+
+
+def test_zero_batch_is_a_no_op(ctx):
+    tp = TablePair(64, params.P0)
+    x = np.arange(64, dtype=np.uint64)
+    a, b = ctx.from_host(x), ctx.from_host(x)
+    ctx.forward_transform_batch(a, b, tp.lib, 0)
+    ctx.inverse_transform_batch(a, b, tp.lib, 0)
+    ctx.forward_transform_rns(a, b, [tp.lib], 0)
+    ctx.polymul_rns(a, a, b, [tp.lib], 0)
+    assert np.array_equal(b.to_host(), x)
+    a.destroy(), b.destroy(), tp.destroy()
+
+
+@pytest.mark.parametrize("n,q", [(2, 113), (4, 113), (8, 113), (16, 769),
+                                 (128, 769), (32, params.Q_KAT_52)])
+def test_small_kat_moduli_at_their_largest_sizes(ctx, n, q):
+    """the reference's tiny KAT moduli (7-, 10-, 52-bit) up to the largest n
+    their 2-adicity allows"""
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(n)
+    x = rand_mod(rng, n, q)
+    assert np.array_equal(run_forward(ctx, x, tp, True), oracle.forward(x, tp.ora))
+    assert np.array_equal(run_inverse(ctx, x, tp, True), oracle.inverse(x, tp.ora))
+    tp.destroy()
+
+
+def test_forward_leaves_tail_and_operand_alone(ctx):
+    n, q = 512, params.Q61
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(3)
+    op = np.concatenate([rand_mod(rng, n, q), rand_u64(rng, 100)])
+    res0 = rand_u64(rng, n + 300)
+    a, b = ctx.from_host(op), ctx.from_host(res0)
+    ctx.forward_transform(a, b, tp.lib)
+    got = b.to_host()
+    assert np.array_equal(got[:n], oracle.forward(op[:n], tp.ora))
+    assert np.array_equal(got[n:], res0[n:])
+    assert np.array_equal(a.to_host(), op)
+    a.destroy(), b.destroy(), tp.destroy()
+
+
+def test_elementwise_in_place_and_odd_lengths(ctx):
+    q = params.P0
+    rng = np.random.default_rng(4)
+    for length in (1, 2, 3, 255, 1025):
+        a, b = rand_u64(rng, length), rand_u64(rng, length)
+        va, vb = ctx.from_host(a), ctx.from_host(b)
+        ctx.elemfma(va, vb, vb, 77, q)          # result aliases b
+        want = oracle.elemfma(a, b, 77, q)
+        assert np.array_equal(vb.to_host(), want)
+        ctx.elemmul(va, va, va, q)              # everything aliases
+        assert np.array_equal(va.to_host(), oracle.elemmul(a, a, q))
+        ctx.elemgtadd(vb, vb, q // 2, 5)
+        assert np.array_equal(vb.to_host(), oracle.elemgtadd(want, q // 2, 5))
+        ctx.elemgtsub(va, va, 3, 4, 1000003)
+        ctx.elemmod(vb, vb, 2, q)
+        va.destroy(), vb.destroy()
+    empty = ctx.vector(0)
+    ctx.elemmul(empty, empty, empty, q)
+    assert empty.to_host().size == 0
+    empty.destroy()
+
+
+def test_asynchronous_ordering_without_syncs(ctx):
+    """many dependent operations enqueued back to back; only the final map
+    synchronises (the reference waits after every single op)"""
+    n, q = 1024, params.P0
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(5)
+    x = rand_mod(rng, n, q)
+    v = ctx.from_host(x)
+    w = ctx.vector(n)
+    for _ in range(25):
+        ctx.forward_transform(v, w, tp.lib)
+        ctx.elemmul(w, w, w, q)
+        ctx.inverse_transform(w, v, tp.lib)
+    want = x
+    for _ in range(25):
+        f = oracle.forward(want, tp.ora)
+        want = oracle.inverse(oracle.elemmul(f, f, q), tp.ora)
+    assert np.array_equal(v.to_host(), want)
+    v.destroy(), w.destroy(), tp.destroy()
+
+
+def test_two_contexts_share_tables(ctx):
+    """tables belong to no context (reference src/ntt_tables.c:65-87); two
+    contexts on the same device use the same tables object"""
+    other = vk.Context(0)
+    tp = TablePair(2048, params.P0)
+    rng = np.random.default_rng(6)
+    x, y = rand_mod(rng, 2048, tp.q), rand_mod(rng, 2048, tp.q)
+    a, b = ctx.from_host(x), other.from_host(y)
+    ctx.forward_transform(a, a, tp.lib)
+    other.forward_transform(b, b, tp.lib)
+    assert np.array_equal(a.to_host(), oracle.forward(x, tp.ora))
+    assert np.array_equal(b.to_host(), oracle.forward(y, tp.ora))
+    a.destroy(), b.destroy()
+    other.destroy()
+    tp.destroy()
+
+
+def test_table_lifetime_and_rns_plan_cache(ctx):
+    """destroying and re-creating tables (possibly at the same address) must
+    not resurrect a cached RNS plan: plans are keyed by table serials"""
+    n = 256
+    rng = np.random.default_rng(7)
+    for round_ in range(4):
+        primes = params.ntt_primes(3 + round_ % 2)[round_ % 2:]
+        tps = [TablePair(n, q) for q in primes]
+        limbs = len(primes)
+        x = np.concatenate([rand_mod(rng, n, primes[p % limbs])
+                            for p in range(limbs * 2)])
+        v = ctx.from_host(x)
+        ctx.forward_transform_rns(v, v, [t.lib for t in tps], 2)
+        assert np.array_equal(
+            v.to_host(), oracle.forward_batch(x, [t.ora for t in tps], 4))
+        v.destroy()
+        for t in tps:
+            t.destroy()
+
+
+@pytest.mark.parametrize("log2n,limbs,batch", [(3, 5, 7), (7, 3, 11),
+                                                (9, 2, 9), (10, 7, 3),
+                                                (15, 2, 3)])
+def test_ragged_rns_shapes(ctx, log2n, limbs, batch):
+    n = 1 << log2n
+    primes = params.ntt_primes(limbs)
+    tps = [TablePair(n, q) for q in primes]
+    rng = np.random.default_rng(limbs * batch)
+    x = np.concatenate([rand_mod(rng, n, primes[p % limbs])
+                        for p in range(limbs * batch)])
+    a, b = ctx.from_host(x), ctx.vector(x.size + 13)
+    ctx.forward_transform_rns(a, b, [t.lib for t in tps], batch)
+    want = oracle.forward_batch(x, [t.ora for t in tps], threads=8)
+    assert np.array_equal(b.to_host()[:x.size], want)
+    ctx.inverse_transform_rns(b, b, [t.lib for t in tps], batch)
+    assert np.array_equal(b.to_host()[:x.size], x)
+    a.destroy(), b.destroy()
+    for t in tps:
+        t.destroy()
+
+
+def test_map_sees_pending_upload_and_kernels(ctx):
+    n = 4096
+    tp = TablePair(n, params.P0)
+    host = vk.host_alloc(n)
+    host.array[:] = np.arange(n, dtype=np.uint64)
+    v = ctx.vector(n, zero=False)
+    v.upload(host)                              # copy stream
+    ctx.forward_transform(v, v, tp.lib)         # compute stream, waits for it
+    got = v.to_host()                           # map: waits for everything
+    assert np.array_equal(got, oracle.forward(host.array, tp.ora))
+    v.destroy(), tp.destroy()
+    host.free()
+
+
+def test_dbgprint_symbols(ctx, capfd):
+    lib = vk.lib()
+    v = ctx.from_host(u64([1, 2, 3]))
+    lib.vkhel_vector_dbgprint(v.handle)
+    t = vk.NttTables(4, 113, 18)
+    lib.vkhel_ntt_tables_dbgprint(t.handle)
+    out = capfd.readouterr().out
+    assert "1, 2, 3" in out
+    assert "ntt_tables: (n=4 q=113 w=18)" in out and "1, 98, 18, 69" in out
+    v.destroy(), t.destroy()
