@@ -504,21 +504,44 @@ ntt_rows_kernel(const fast_pass p) {
 			if (rr > 0) {
 				/* redistribute: previous round's layout -> this round's */
 				const int prev = INV ? r + 1 : r - 1;
+				/* where registers (e, e+1) are adjacent coefficients (the
+				 * deepest round) the exchange moves 128 bits at a time: half
+				 * the shared-memory instructions and half the bank conflicts
+				 * of that layout's 32-byte lane stride */
 				u64 *xw = xb + xpad(G::tbase(prev, t));
 #pragma unroll
 				for (int pp = 0; pp < NP; pp++) {
+					if (G::eoff(prev, 1) == 1) {
 #pragma unroll
-					for (int e = 0; e < 8; e++) {
-						xw[pp * C::xbuf + xpad(G::eoff(prev, e))] = x[pp][e];
+						for (int e = 0; e < 8; e += 2) {
+							*(ulonglong2 *) (xw + pp * C::xbuf
+									+ xpad(G::eoff(prev, e))) =
+								make_ulonglong2(x[pp][e], x[pp][e + 1]);
+						}
+					} else {
+#pragma unroll
+						for (int e = 0; e < 8; e++) {
+							xw[pp * C::xbuf + xpad(G::eoff(prev, e))] = x[pp][e];
+						}
 					}
 				}
 				__syncwarp();
 				const u64 *xr = xb + xpad(G::tbase(r, t));
 #pragma unroll
 				for (int pp = 0; pp < NP; pp++) {
+					if (G::eoff(r, 1) == 1) {
 #pragma unroll
-					for (int e = 0; e < 8; e++) {
-						x[pp][e] = xr[pp * C::xbuf + xpad(G::eoff(r, e))];
+						for (int e = 0; e < 8; e += 2) {
+							const ulonglong2 v = *(const ulonglong2 *) (xr
+									+ pp * C::xbuf + xpad(G::eoff(r, e)));
+							x[pp][e] = v.x;
+							x[pp][e + 1] = v.y;
+						}
+					} else {
+#pragma unroll
+						for (int e = 0; e < 8; e++) {
+							x[pp][e] = xr[pp * C::xbuf + xpad(G::eoff(r, e))];
+						}
 					}
 				}
 			}
