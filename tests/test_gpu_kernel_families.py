@@ -1,0 +1,33 @@
+"""GPU suite: the three NTT kernel families on the same moduli.
+
+By default q < 2^64/6 runs the approximate-quotient butterflies, larger
+q < 2^62 the exact-quotient ones and q >= 2^62 (or n < 8) the generic kernel.
+The environment switches $VKHEL_EXACT_QUOTIENT and $VKHEL_FORCE_GENERIC force
+the slower families for every modulus; they are read once per process, so the
+parity tests are re-run in child processes."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
+          "or rns_matches or polymul or inverse_scales_tail")
+
+
+@pytest.mark.parametrize("switch", ["VKHEL_EXACT_QUOTIENT",
+                                    "VKHEL_FORCE_GENERIC"])
+def test_parity_with_forced_family(switch):
+    env = dict(os.environ)
+    env[switch] = "1"
+    res = subprocess.run(
+        [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
+         "-p", "no:cacheprovider", "-k", SELECT,
+         os.path.join(ROOT, "tests", "test_gpu_parity.py")],
+        env=env, capture_output=True, text=True, timeout=1200, cwd=ROOT)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-4000:]
+    assert " passed" in res.stdout

@@ -306,6 +306,44 @@ struct gs_v16 { static const char *name() { return "GS v16 = v12, t = d*w + hi*(
 		y = d * c.w + __umul64hi(d, c.wp) * nq;
 	} };
 
+/* ---- V18: v14 without the a0*b0 partial product: h' in {hi-1, hi}, t in [0,3q),
+ * values in [0,6q), one csub(x, 3q); needs 6q < 2^64 ---- */
+__device__ __forceinline__ u64 mulhi_chain_approx(u64 a, u64 b) {
+	const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+	u32 r1, r2;
+	asm("{\n\t"
+		".reg .u32 r0;\n\t"
+		"mul.lo.u32 r0, %2, %5;\n\t"
+		"mul.hi.u32 %0, %2, %5;\n\t"
+		"mad.lo.cc.u32 r0, %3, %4, r0;\n\t"
+		"madc.hi.cc.u32 %0, %3, %4, %0;\n\t"
+		"addc.u32 %1, 0, 0;\n\t"
+		"mad.lo.cc.u32 %0, %3, %5, %0;\n\t"
+		"madc.hi.u32 %1, %3, %5, %1;\n\t"
+		"}" : "=&r"(r1), "=&r"(r2) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+	return ((u64) r2 << 32) | r1;
+}
+struct ct_v18 { static const char *name() { return "CT v18 = v14 minus lo*lo product, csub(x,3q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q;
+		const u64 xr = csub_borrow(x, threeq);
+		const u64 t = y * c.w - mulhi_chain_approx(y, c.wp) * c.q;
+		x = xr + t; y = xr - t + threeq;
+	} };
+struct gs_v18 { static const char *name() { return "GS v18 approx chain, range [0,3q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q;
+		const u64 s = x + y, d = x - y + threeq;
+		x = csub_borrow(s, threeq);
+		y = d * c.w - mulhi_chain_approx(d, c.wp) * c.q;
+	} };
+struct gs_v14 { static const char *name() { return "GS v14 exact chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 s = x + y, d = x - y + c.twoq;
+		x = csub_borrow(s, c.twoq);
+		y = d * c.w - mulhi_chain(d, c.wp) * c.q;
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -385,7 +423,7 @@ int main() {
 		run<ct_v0>(sms, c);
 	}
 	g_threads = 1024;
-	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v14>(sms, c); run<ct_v16>(sms, c); run<ct_v17>(sms, c); run<gs_v12>(sms, c); run<gs_v16>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v14>(sms, c); run<ct_v18>(sms, c); run<ct_v16>(sms, c); run<ct_v17>(sms, c); run<gs_v12>(sms, c); run<gs_v14>(sms, c); run<gs_v18>(sms, c); run<gs_v16>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);

@@ -370,7 +370,7 @@ struct row_cfg {
 /* Row pass.  CTA = (batch chunk, limb, H group): `bchunk` batch entries of
  * 2^hgroup_log2 consecutive tiles sharing one staged twiddle set.  A warp-group
  * of 2^(K-3) lanes carries NP batch entries of one tile position at a time. */
-template <bool INV, int K, int NP, bool MUL>
+template <bool INV, int K, int NP, bool MUL, bool APX>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const fast_pass p) {
@@ -396,7 +396,7 @@ ntt_rows_kernel(const fast_pass p) {
 	const unsigned H0 = hg << p.hgroup_log2;
 
 	const limb_desc &d = p.descs[limb];
-	const u64 q = d.q, twoq = 2 * q;
+	const u64 q = d.q, bq = APX ? 3 * q : 2 * q;   /* butterfly bound */
 	__shared__ __align__(8) u64 tw_bar;
 	if (threadIdx.x == 0) {
 		mbar_init(&tw_bar, 1);
@@ -546,9 +546,9 @@ ntt_rows_kernel(const fast_pass p) {
 				}
 			}
 			if (fold) {
-				tile_round<K, INV, true, NP>(x, r, t, twt, q, twoq, fold_a, fold_b);
+				tile_round<K, INV, true, NP, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
 			} else {
-				tile_round<K, INV, false, NP>(x, r, t, twt, q, twoq, fold_a, fold_b);
+				tile_round<K, INV, false, NP, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
 			}
 		}
 		__syncwarp();   /* the exchange buffer is reused by the next item */
@@ -560,10 +560,7 @@ ntt_rows_kernel(const fast_pass p) {
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					if (canon) {
-						if (!INV) {
-							x[pp][e] = csub(x[pp][e], twoq);
-						}
-						x[pp][e] = csub(x[pp][e], q);
+						x[pp][e] = tile_canon<INV, APX>(x[pp][e], q, bq);
 					}
 				}
 				if (G::eoff(last, 1) == 1) {
@@ -600,7 +597,7 @@ template <int NP> struct col_vec;
 template <> struct col_vec<1> { typedef u64 type; };
 template <> struct col_vec<2> { typedef ulonglong2 type; };
 
-template <bool INV, int K, int CL, int NP>
+template <bool INV, int K, int CL, int NP, bool APX>
 __global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
 		((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
 			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) > 0
@@ -626,7 +623,7 @@ ntt_cols_kernel(const fast_pass p) {
 	const u64 poly = blk >> s0;
 
 	const limb_desc &d = p.descs[poly % p.limbs];
-	const u64 q = d.q, twoq = 2 * q;
+	const u64 q = d.q, bq = APX ? 3 * q : 2 * q;   /* butterfly bound */
 
 	const int c = (threadIdx.x & ((1 << C::cthreads_log2) - 1)) * NP;
 	const int t = threadIdx.x >> C::cthreads_log2;         /* row group */
@@ -697,9 +694,9 @@ ntt_cols_kernel(const fast_pass p) {
 			}
 		}
 		if (fold) {
-			tile_round<K, INV, true, NP>(x, r, t, sm_tw, q, twoq, fold_a, fold_b);
+			tile_round<K, INV, true, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
 		} else {
-			tile_round<K, INV, false, NP>(x, r, t, sm_tw, q, twoq, fold_a, fold_b);
+			tile_round<K, INV, false, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
 		}
 	}
 
@@ -711,7 +708,7 @@ ntt_cols_kernel(const fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			u64 w = x[pp][e];
 			if (canon) {
-				w = csub(w, q);
+				w = tile_canon<true, APX>(w, q, bq);
 			}
 			((u64 *) &v)[pp] = w;
 		}
@@ -719,7 +716,7 @@ ntt_cols_kernel(const fast_pass p) {
 	}
 }
 
-template <bool INV, int K, int NP, bool MUL>
+template <bool INV, int K, int NP, bool MUL, bool APX>
 static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	using C = row_cfg<K>;
 	const u64 batch = p.polys / p.limbs;
@@ -749,34 +746,34 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
 	if (smem > 48 * 1024) {
 		/* per device, and cheap: set it on every such launch */
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP, MUL>,
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP, MUL, APX>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	ntt_rows_kernel<INV, K, NP, MUL><<<(unsigned) blocks, FAST_THREADS, smem,
+	ntt_rows_kernel<INV, K, NP, MUL, APX><<<(unsigned) blocks, FAST_THREADS, smem,
 		ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	ctx->dev.launches++;
 }
 
-template <bool INV, int K>
+template <bool INV, int K, bool APX>
 static void run_rows(struct vkhel_ctx *ctx, const fast_pass &p) {
 	if constexpr (INV) {
 		if (p.src2) {
-			run_rows_np<INV, K, 1, true>(ctx, p);
+			run_rows_np<INV, K, 1, true, APX>(ctx, p);
 			return;
 		}
 	}
 	/* two batch entries per thread when there are two to pair up */
 	if constexpr (ROWS_NP == 2) {
 		if (p.polys / p.limbs >= 2) {
-			run_rows_np<INV, K, 2, false>(ctx, p);
+			run_rows_np<INV, K, 2, false, APX>(ctx, p);
 			return;
 		}
 	}
-	run_rows_np<INV, K, 1, false>(ctx, p);
+	run_rows_np<INV, K, 1, false, APX>(ctx, p);
 }
 
-template <bool INV, int K, int CL, int NP>
+template <bool INV, int K, int CL, int NP, bool APX>
 static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	using C = col_cfg<K, CL, NP>;
 	const unsigned low_bits = p.log2n - p.s0 - K;
@@ -786,10 +783,10 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
 	if (smem > 48 * 1024) {
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel<INV, K, CL, NP>,
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel<INV, K, CL, NP, APX>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	ntt_cols_kernel<INV, K, CL, NP><<<(unsigned) blocks, C::threads, smem,
+	ntt_cols_kernel<INV, K, CL, NP, APX><<<(unsigned) blocks, C::threads, smem,
 		ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());
 	ctx->dev.launches++;
@@ -798,55 +795,55 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 /* 256 threads per CTA: 2^(12-K) columns with two columns per thread, 2^(11-K)
  * with one; the 8-point column pass of n = 2^9 and 2^10 has only 64 / 128
  * columns to offer and runs with fewer threads */
-template <bool INV, int K>
+template <bool INV, int K, bool APX>
 static void run_cols(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const unsigned low_bits = p.log2n - p.s0 - K;
 	if constexpr (COLS_NP == 2 && K <= 8) {
 		if (low_bits >= 12 - K) {
-			run_cols_cl<INV, K, 12 - K, 2>(ctx, p);
+			run_cols_cl<INV, K, 12 - K, 2, APX>(ctx, p);
 			return;
 		}
 	}
 	if constexpr (K >= 9) {
 		/* 512- and 1024-point column tiles (n = 2^17, 2^18): 8 columns,
 		 * 512 / 1024 threads */
-		run_cols_cl<INV, K, 3, 1>(ctx, p);
+		run_cols_cl<INV, K, 3, 1, APX>(ctx, p);
 	} else if (low_bits >= 11 - K) {
-		run_cols_cl<INV, K, 11 - K, 1>(ctx, p);
+		run_cols_cl<INV, K, 11 - K, 1, APX>(ctx, p);
 	} else if (K == 3 && low_bits == 7) {
-		run_cols_cl<INV, 3, 7, 1>(ctx, p);
+		run_cols_cl<INV, 3, 7, 1, APX>(ctx, p);
 	} else if (K == 3 && low_bits == 6) {
-		run_cols_cl<INV, 3, 6, 1>(ctx, p);
+		run_cols_cl<INV, 3, 6, 1, APX>(ctx, p);
 	} else {
 		VK_DIE("internal: no column kernel for K=%d, row stride 2^%u", K,
 				low_bits);
 	}
 }
 
-template <bool INV>
+template <bool INV, bool APX>
 static void run_rows_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
 	switch (k) {
-	case 3: run_rows<INV, 3>(ctx, p); break;
-	case 4: run_rows<INV, 4>(ctx, p); break;
-	case 5: run_rows<INV, 5>(ctx, p); break;
-	case 6: run_rows<INV, 6>(ctx, p); break;
-	case 7: run_rows<INV, 7>(ctx, p); break;
-	case 8: run_rows<INV, 8>(ctx, p); break;
+	case 3: run_rows<INV, 3, APX>(ctx, p); break;
+	case 4: run_rows<INV, 4, APX>(ctx, p); break;
+	case 5: run_rows<INV, 5, APX>(ctx, p); break;
+	case 6: run_rows<INV, 6, APX>(ctx, p); break;
+	case 7: run_rows<INV, 7, APX>(ctx, p); break;
+	case 8: run_rows<INV, 8, APX>(ctx, p); break;
 	default: VK_DIE("internal: row pass of %u stages", k);
 	}
 }
 
-template <bool INV>
+template <bool INV, bool APX>
 static void run_cols_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
 	switch (k) {
-	case 3: run_cols<INV, 3>(ctx, p); break;
-	case 4: run_cols<INV, 4>(ctx, p); break;
-	case 5: run_cols<INV, 5>(ctx, p); break;
-	case 6: run_cols<INV, 6>(ctx, p); break;
-	case 7: run_cols<INV, 7>(ctx, p); break;
-	case 8: run_cols<INV, 8>(ctx, p); break;
-	case 9: run_cols<INV, 9>(ctx, p); break;
-	case 10: run_cols<INV, 10>(ctx, p); break;
+	case 3: run_cols<INV, 3, APX>(ctx, p); break;
+	case 4: run_cols<INV, 4, APX>(ctx, p); break;
+	case 5: run_cols<INV, 5, APX>(ctx, p); break;
+	case 6: run_cols<INV, 6, APX>(ctx, p); break;
+	case 7: run_cols<INV, 7, APX>(ctx, p); break;
+	case 8: run_cols<INV, 8, APX>(ctx, p); break;
+	case 9: run_cols<INV, 9, APX>(ctx, p); break;
+	case 10: run_cols<INV, 10, APX>(ctx, p); break;
 	default: VK_DIE("internal: column pass of %u stages", k);
 	}
 }
@@ -871,7 +868,7 @@ static fast_plan plan_fast(unsigned log2n) {
 	return pl;
 }
 
-template <bool INV>
+template <bool INV, bool APX>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, const u64 *src2 = NULL) {
@@ -906,24 +903,24 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 			p.src = cur;
 			p.dst = dst;
 			p.s0 = pl.lead;
-			run_cols_k<false>(ctx, p, pl.kcol);
+			run_cols_k<false, APX>(ctx, p, pl.kcol);
 			cur = dst;
 		}
 		p.src = cur;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
-		run_rows_k<false>(ctx, p, pl.krow);
+		run_rows_k<false, APX>(ctx, p, pl.krow);
 	} else {
 		p.src = src;
 		p.src2 = src2;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
-		run_rows_k<true>(ctx, p, pl.krow);
+		run_rows_k<true, APX>(ctx, p, pl.krow);
 		p.src2 = NULL;
 		if (pl.kcol) {
 			p.src = dst;
 			p.s0 = pl.lead;
-			run_cols_k<true>(ctx, p, pl.kcol);
+			run_cols_k<true, APX>(ctx, p, pl.kcol);
 		}
 		if (pl.lead) {
 			lead.src = dst;
@@ -937,6 +934,16 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 /* ======================================================================================
  * Dispatch
  * ====================================================================================== */
+/* The approximate-quotient butterflies keep forward values below 6q, so they
+ * need 6q < 2^64; they are not combined with the leading generic pass of
+ * n > 2^18, whose inverse expects values below 2q. */
+static bool use_approx(uint64_t q_max, unsigned log2n) {
+	/* $VKHEL_EXACT_QUOTIENT forces the exact-quotient kernels (tests run
+	 * both families on the same moduli) */
+	static const bool force_exact = getenv("VKHEL_EXACT_QUOTIENT") != NULL;
+	return !force_exact && q_max < 0xffffffffffffffffull / 6 && log2n <= 18;
+}
+
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, uint64_t q_max) {
@@ -944,9 +951,15 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 			log2n);
 	VK_REQUIRE(q_max < (1ull << 63), "NTT modulus must be below 2^63");
 	const bool strict = q_max >= (1ull << 62);
-	if (!strict && log2n >= 3 && !getenv("VKHEL_FORCE_GENERIC")) {
-		if (inverse) run_fast<true>(ctx, src, dst, descs, limbs, polys, log2n);
-		else run_fast<false>(ctx, src, dst, descs, limbs, polys, log2n);
+	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
+	if (!strict && log2n >= 3 && !force_generic) {
+		if (use_approx(q_max, log2n)) {
+			if (inverse) run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n);
+			else run_fast<false, true>(ctx, src, dst, descs, limbs, polys, log2n);
+		} else {
+			if (inverse) run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n);
+			else run_fast<false, false>(ctx, src, dst, descs, limbs, polys, log2n);
+		}
 		return;
 	}
 	if (inverse) {
@@ -961,9 +974,14 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max) {
-	if (q_max >= (1ull << 62) || log2n < 3 || getenv("VKHEL_FORCE_GENERIC")) {
+	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
+	if (q_max >= (1ull << 62) || log2n < 3 || force_generic) {
 		return false;   /* generic path: no fused product */
 	}
-	run_fast<true>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+	if (use_approx(q_max, log2n)) {
+		run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+	} else {
+		run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+	}
 	return true;
 }

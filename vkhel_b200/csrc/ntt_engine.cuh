@@ -26,8 +26,10 @@
  * butterflies/clk/SM with an LDS.128 per butterfly against 2.85 without), is
  * then paid once per two butterflies.
  *
- * Arithmetic: Harvey lazy butterflies (modarith.cuh).  Forward values stay in
- * [0,4q), inverse values in [0,2q); q < 2^62.
+ * Arithmetic: Harvey lazy butterflies (modarith.cuh).  Exact quotient (APX =
+ * false, q < 2^62): forward values stay in [0,4q), inverse values in [0,2q).
+ * Approximate quotient (APX = true, 6q < 2^64): [0,6q) and [0,3q).  `bq` is
+ * the butterfly's bound, 2q or 3q.
  */
 #ifndef VKHEL_NTT_ENGINE_CUH
 #define VKHEL_NTT_ENGINE_CUH
@@ -90,10 +92,11 @@ struct tile_geom {
  * columns): every (w, w') pair fetched from shared memory feeds NP butterflies.
  *   twt: the tile's twiddle subtree in shared memory, twt[node] = (w, w')
  *   FOLD: inverse only -- local stage 0 is global stage 0: multiply by n^-1
- *         (fold_a = n^-1, fold_b = inv_root[1] * n^-1) instead of node 1. */
-template <int K, bool INV, bool FOLD, int NP>
+ *         (fold_a = n^-1, fold_b = inv_root[1] * n^-1) instead of node 1.
+ *   APX:  butterflies around the approximate Shoup product (bq = 3q) */
+template <int K, bool INV, bool FOLD, int NP, bool APX>
 __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
-		const ulonglong2 *twt, u64 q, u64 twoq, ulonglong2 fold_a,
+		const ulonglong2 *twt, u64 q, u64 bq, ulonglong2 fold_a,
 		ulonglong2 fold_b) {
 	using G = tile_geom<K>;
 	const int cnt = G::cnt(r);
@@ -117,9 +120,14 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 					u64 &X = x[p][e];
 					u64 &Y = x[p][e | (1 << beta)];
 					const u64 s = X + Y;
-					const u64 d = X - Y + twoq;
-					X = shoup_lazy(s, fold_a.x, fold_a.y, q);
-					Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
+					const u64 d = X - Y + bq;
+					if (APX) {
+						X = shoup_lazy3(s, fold_a.x, fold_a.y, q);
+						Y = shoup_lazy3(d, fold_b.x, fold_b.y, q);
+					} else {
+						X = shoup_lazy(s, fold_a.x, fold_a.y, q);
+						Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
+					}
 				}
 			} else {
 				const ulonglong2 w = twp[G::goff(r, j, e)];
@@ -128,14 +136,29 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 					u64 &X = x[p][e];
 					u64 &Y = x[p][e | (1 << beta)];
 					if (INV) {
-						gs_lazy(X, Y, w.x, w.y, q, twoq);
+						if (APX) gs_lazy3(X, Y, w.x, w.y, q, bq);
+						else gs_lazy(X, Y, w.x, w.y, q, bq);
 					} else {
-						ct_lazy(X, Y, w.x, w.y, q, twoq);
+						if (APX) ct_lazy3(X, Y, w.x, w.y, q, bq);
+						else ct_lazy(X, Y, w.x, w.y, q, bq);
 					}
 				}
 			}
 		}
 	}
+}
+
+/* canonical residue of a value at the end of a transform: forward values are
+ * below 2*bq, inverse values below bq (bq = 2q exact, 3q approximate) */
+template <bool INV, bool APX>
+__device__ __forceinline__ u64 tile_canon(u64 v, u64 q, u64 bq) {
+	if (!INV) {
+		v = csub(v, bq);        /* [0,2bq) -> [0,bq) */
+	}
+	if (APX) {
+		v = csub(v, q);         /* [0,3q) -> [0,2q) */
+	}
+	return csub(v, q);
 }
 
 #endif
