@@ -40,7 +40,7 @@ E2E_CHUNKS = 4
 POLYS = LIMBS * BATCH
 METRIC = "64-bit NTTs/sec at n=2^16"
 # measured per-GPU integer peaks (profiles/r01_bfly_bench.txt)
-BFLY_PEAK_G = 874.0          # lazy Harvey butterflies/s, best compiled form (v14)
+BFLY_PEAK_G = 1038.0         # lazy Harvey butterflies/s, best compiled form (v19)
 BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
 # DRAM bytes of one step (4 launches) from the ncu --set full capture
 # profiles/r01_ntt_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
@@ -399,10 +399,11 @@ def run_native_arm(args):
             "bound": "imad (fmaheavy pipe)", "achieved": bfly_rate,
             "peak": BFLY_PEAK_G, "unit": "G butterflies/s",
             "frac": bfly_rate / BFLY_PEAK_G,
-            "peak_source": "tools/bfly_bench.cu v14 (the library's butterfly: "
-                           "borrow-chain csub, mad/madc mulhi; twiddles in "
-                           "uniform registers, no memory): 3.00 per clk per "
-                           "SM x 148 SMs x 1.965 GHz",
+            "peak_source": "tools/bfly_bench.cu v19 (the library's butterfly: "
+                           "borrow-chain csub, approximate-quotient Shoup "
+                           "product as one PTX mad chain; twiddles in uniform "
+                           "registers, no memory): 3.57 per clk per SM x 148 "
+                           "SMs x 1.965 GHz",
             "pure_multiplier_bound": BFLY_MULT_BOUND_G,
         }
         if world == 1 and not args.no_cpu:

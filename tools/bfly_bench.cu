@@ -344,6 +344,49 @@ struct gs_v14 { static const char *name() { return "GS v14 exact chain"; }
 		y = d * c.w - mulhi_chain(d, c.wp) * c.q;
 	} };
 
+/* ---- V19: v18 with the low 64 bits y*w + h*(2^64-q) as one explicit mad chain ---- */
+__device__ __forceinline__ u64 shoup3_ptx(u64 y, u64 w, u64 wp, u64 nq) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) w, w1 = (u32) (w >> 32);
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32), n0 = (u32) nq, n1 = (u32) (nq >> 32);
+	u32 t0, t1;
+	asm("{\n\t"
+		".reg .u32 r0, h0, h1;\n\t"
+		/* h = approximate high 64 bits of y * wp */
+		"mul.lo.u32 r0, %2, %7;\n\t"
+		"mul.hi.u32 h0, %2, %7;\n\t"
+		"mad.lo.cc.u32 r0, %3, %6, r0;\n\t"
+		"madc.hi.cc.u32 h0, %3, %6, h0;\n\t"
+		"addc.u32 h1, 0, 0;\n\t"
+		"mad.lo.cc.u32 h0, %3, %7, h0;\n\t"
+		"madc.hi.u32 h1, %3, %7, h1;\n\t"
+		/* t = lo64(y*w) + lo64(h*nq) */
+		"mul.lo.u32 %0, %2, %4;\n\t"
+		"mul.hi.u32 %1, %2, %4;\n\t"
+		"mad.lo.cc.u32 %0, h0, %8, %0;\n\t"
+		"madc.hi.u32 %1, h0, %8, %1;\n\t"
+		"mad.lo.u32 %1, %2, %5, %1;\n\t"
+		"mad.lo.u32 %1, %3, %4, %1;\n\t"
+		"mad.lo.u32 %1, h0, %9, %1;\n\t"
+		"mad.lo.u32 %1, h1, %8, %1;\n\t"
+		"}" : "=&r"(t0), "=&r"(t1)
+		: "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1));
+	return ((u64) t1 << 32) | t0;
+}
+struct ct_v19 { static const char *name() { return "CT v19 = v18, whole Shoup product as one PTX chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, threeq);
+		const u64 t = shoup3_ptx(y, c.w, c.wp, nq);
+		x = xr + t; y = xr - t + threeq;
+	} };
+struct gs_v19 { static const char *name() { return "GS v19 whole Shoup product as one PTX chain"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 s = x + y, d = x - y + threeq;
+		x = csub_borrow(s, threeq);
+		y = shoup3_ptx(d, c.w, c.wp, nq);
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -423,7 +466,7 @@ int main() {
 		run<ct_v0>(sms, c);
 	}
 	g_threads = 1024;
-	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v14>(sms, c); run<ct_v18>(sms, c); run<ct_v16>(sms, c); run<ct_v17>(sms, c); run<gs_v12>(sms, c); run<gs_v14>(sms, c); run<gs_v18>(sms, c); run<gs_v16>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
+	run<ct_v0>(sms, c); run<ct_v8>(sms, c); run<ct_v9>(sms, c); run<ct_v12>(sms, c); run<ct_v14>(sms, c); run<ct_v18>(sms, c); run<ct_v19>(sms, c); run<gs_v19>(sms, c); run<ct_v16>(sms, c); run<ct_v17>(sms, c); run<gs_v12>(sms, c); run<gs_v14>(sms, c); run<gs_v18>(sms, c); run<gs_v16>(sms, c); run<ct_v1>(sms, c); run<ct_v2>(sms, c); run<ct_v3>(sms, c);
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);
