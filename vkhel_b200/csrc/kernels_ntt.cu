@@ -279,6 +279,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef ROWS_PREFETCH
 #define ROWS_PREFETCH 1
 #endif
+#ifndef FAST_PDL
+#define FAST_PDL 1
+#endif
 
 struct fast_pass {
 	const u64 *src;
@@ -298,6 +301,43 @@ struct fast_pass {
  * Additive over disjoint bit fields, like the tile index itself. */
 __host__ __device__ constexpr int xpad(int i) {
 	return i + ((i >> 5) << 2);
+}
+
+/* ---- programmatic dependent launch (PDL) ------------------------------------------
+ * The fast kernels are launched with programmaticStreamSerialization: a CTA of
+ * the next kernel may start once every CTA of the current one has executed
+ * pdl_launch_dependents() (or exited), runs its prologue -- barrier init and
+ * the TMA staging of its twiddles, which do not depend on the previous kernel
+ * -- and blocks in pdl_wait() until the previous kernel has completed and its
+ * writes are visible.  This overlaps one kernel's prologue with the tail of
+ * the one before it. */
+__device__ __forceinline__ void pdl_wait() {
+#if FAST_PDL
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if FAST_PDL
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <class... KArgs, class... Args>
+static void launch_fast(struct vkhel_ctx *ctx, void (*kernel)(KArgs...),
+		unsigned grid, unsigned block, size_t smem, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = ctx_stream(ctx);
+	cudaLaunchAttribute attr;
+	attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr.val.programmaticStreamSerializationAllowed = FAST_PDL;
+	cfg.attrs = &attr;
+	cfg.numAttrs = 1;
+	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
+	ctx->dev.launches++;
 }
 
 /* ---- twiddle staging by TMA bulk copies --------------------------------------------
@@ -407,6 +447,7 @@ ntt_rows_kernel(const fast_pass p) {
 				hgroup, &tw_bar);
 	}
 	bool tw_ready = false;
+	pdl_wait();   /* the coefficients come from the previous kernel */
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int t = lane & (C::group - 1);                 /* thread within group */
@@ -552,6 +593,9 @@ ntt_rows_kernel(const fast_pass p) {
 			}
 		}
 		__syncwarp();   /* the exchange buffer is reused by the next item */
+		if (base + C::groups_per_cta >= nitems) {
+			pdl_launch_dependents();   /* only this CTA's last stores remain */
+		}
 
 #pragma unroll
 		for (int pp = 0; pp < NP; pp++) {
@@ -631,6 +675,16 @@ ntt_cols_kernel(const fast_pass p) {
 	constexpr int last = INV ? 0 : G::rounds - 1;
 	const u64 base = (poly << L) + (H << (L - s0)) + (cg << CL) + c;
 
+	__shared__ __align__(8) u64 tw_bar;
+	if (threadIdx.x == 0) {
+		mbar_init(&tw_bar, 1);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
+				&tw_bar);
+	}
+	pdl_wait();   /* the coefficients come from the previous kernel */
 	u64 x[NP][8];
 	{
 		const u64 *sp = p.src + base + ((u64) G::tbase(first, t) << low_bits);
@@ -644,15 +698,6 @@ ntt_cols_kernel(const fast_pass p) {
 				x[0][e] = ((const u64 *) &v)[0];
 			}
 		}
-	}
-	__shared__ __align__(8) u64 tw_bar;
-	if (threadIdx.x == 0) {
-		mbar_init(&tw_bar, 1);
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
-				&tw_bar);
 	}
 	const bool fold = INV && s0 == 0;
 	/* the forward transform always ends in a row pass; the inverse ends here
@@ -700,6 +745,7 @@ ntt_cols_kernel(const fast_pass p) {
 		}
 	}
 
+	pdl_launch_dependents();   /* only this CTA's stores remain */
 	u64 *dp = p.dst + base + ((u64) G::tbase(last, t) << low_bits);
 #pragma unroll
 	for (int e = 0; e < 8; e++) {
@@ -749,10 +795,8 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP, MUL, APX>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	ntt_rows_kernel<INV, K, NP, MUL, APX><<<(unsigned) blocks, FAST_THREADS, smem,
-		ctx_stream(ctx)>>>(p);
-	CUDA_CHECK(cudaGetLastError());
-	ctx->dev.launches++;
+	launch_fast(ctx, ntt_rows_kernel<INV, K, NP, MUL, APX>, (unsigned) blocks,
+			FAST_THREADS, smem, p);
 }
 
 template <bool INV, int K, bool APX>
@@ -786,10 +830,8 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 		CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel<INV, K, CL, NP, APX>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	ntt_cols_kernel<INV, K, CL, NP, APX><<<(unsigned) blocks, C::threads, smem,
-		ctx_stream(ctx)>>>(p);
-	CUDA_CHECK(cudaGetLastError());
-	ctx->dev.launches++;
+	launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX>, (unsigned) blocks,
+			C::threads, smem, p);
 }
 
 /* 256 threads per CTA: 2^(12-K) columns with two columns per thread, 2^(11-K)
