@@ -44,8 +44,8 @@ BFLY_PEAK_G = 1038.0         # lazy Harvey butterflies/s, best compiled form (v1
 BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
 # DRAM bytes of one step (4 launches) from the ncu --set full capture
 # profiles/r01_ntt_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
-NCU_TRAFFIC_BYTES_PER_STEP = int((268.621 + 219.618 + 302.085 + 218.647
-                                  + 302.334 + 215.959 + 268.645 + 208.700) * 1e6)
+NCU_TRAFFIC_BYTES_PER_STEP = int((268.604 + 220.467 + 303.027 + 212.954
+                                  + 302.851 + 215.881 + 269.238 + 215.945) * 1e6)
 WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
             "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
             "step = forward + inverse of the whole batch")

@@ -282,6 +282,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef FAST_PDL
 #define FAST_PDL 1
 #endif
+#ifndef FAST_PDL_EARLY
+#define FAST_PDL_EARLY 0
+#endif
 
 struct fast_pass {
 	const u64 *src;
@@ -448,6 +451,9 @@ ntt_rows_kernel(const fast_pass p) {
 	}
 	bool tw_ready = false;
 	pdl_wait();   /* the coefficients come from the previous kernel */
+#if FAST_PDL_EARLY
+	pdl_launch_dependents();
+#endif
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int t = lane & (C::group - 1);                 /* thread within group */
@@ -685,6 +691,9 @@ ntt_cols_kernel(const fast_pass p) {
 				&tw_bar);
 	}
 	pdl_wait();   /* the coefficients come from the previous kernel */
+#if FAST_PDL_EARLY
+	pdl_launch_dependents();
+#endif
 	u64 x[NP][8];
 	{
 		const u64 *sp = p.src + base + ((u64) G::tbase(first, t) << low_bits);
