@@ -121,13 +121,11 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 					u64 &Y = x[p][e | (1 << beta)];
 					const u64 s = X + Y;
 					const u64 d = X - Y + bq;
-					if (APX) {
-						X = shoup_lazy3(s, fold_a.x, fold_a.y, q);
-						Y = shoup_lazy3(d, fold_b.x, fold_b.y, q);
-					} else {
-						X = shoup_lazy(s, fold_a.x, fold_a.y, q);
-						Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
-					}
+					/* exact quotient here even in the approximate family: the
+					 * outputs of this stage are the transform's outputs, and
+					 * [0,2q) needs one conditional subtraction instead of two */
+					X = shoup_lazy(s, fold_a.x, fold_a.y, q);
+					Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
 				}
 			} else {
 				const ulonglong2 w = twp[G::goff(r, j, e)];
@@ -154,10 +152,11 @@ template <bool INV, bool APX>
 __device__ __forceinline__ u64 tile_canon(u64 v, u64 q, u64 bq) {
 	if (!INV) {
 		v = csub(v, bq);        /* [0,2bq) -> [0,bq) */
+		if (APX) {
+			v = csub(v, q);     /* [0,3q) -> [0,2q) */
+		}
 	}
-	if (APX) {
-		v = csub(v, q);         /* [0,3q) -> [0,2q) */
-	}
+	/* inverse: the folded last stage leaves [0,2q) in both families */
 	return csub(v, q);
 }
 
