@@ -338,7 +338,7 @@ def run_native_arm(args):
     ms_inv, _ = timed(inv_only, args.steps, 1)
 
     host_out.array[:] = 0
-    e2e_steps = max(2, min(args.steps, 10))
+    e2e_steps = max(2, min(args.steps, 20))
     ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
     ok = ok and bool(np.array_equal(host_out.array, host_in.array))
 
@@ -430,8 +430,8 @@ def run_native_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg")
