@@ -14,6 +14,7 @@ extern "C" {
 #endif
 
 #define VKHEL_PINNED_SLOTS 8
+#define VKHEL_FORK_EVENTS 4
 
 struct pinned_slot {
 	void *ptr;
@@ -30,6 +31,15 @@ struct device_ctx {
 	void *stream_h2d;    /* vkhel_vector_upload: host -> device copy engine */
 	void *stream_d2h;    /* vkhel_vector_download: device -> host copy engine */
 	void *ev_scratch;    /* cudaEvent_t used to fork from the compute stream */
+	/* Every use of a vector on the compute stream takes the next serial
+	 * number; fork_ev[i] was recorded on the compute stream when the serial
+	 * stood at fork_serial[i], so it covers every use up to that number.  A
+	 * transfer of a vector waits for the oldest of these that covers the
+	 * vector's last use -- not for unrelated kernels enqueued after it. */
+	uint64_t op_serial;
+	void *fork_ev[VKHEL_FORK_EVENTS];
+	uint64_t fork_serial[VKHEL_FORK_EVENTS];
+	int fork_next;
 	void *mem_pool;      /* cudaMemPool_t: stream-ordered allocator */
 	struct pinned_slot pinned[VKHEL_PINNED_SLOTS]; /* map() staging cache */
 	void *flush_buf;     /* L2 flush scratch, allocated on demand */

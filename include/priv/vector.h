@@ -34,6 +34,12 @@ struct vkhel_vector {
 	 * wait for it */
 	void *xfer_event;   /* cudaEvent_t, created on first use */
 	int xfer_pending;
+	/* serial number (device_ctx.op_serial) of the last operation enqueued on
+	 * the compute stream that touched this vector; `exposed` once the raw
+	 * device pointer has been handed out (then every transfer orders itself
+	 * after everything on the compute stream) */
+	uint64_t last_op;
+	int exposed;
 };
 
 void vkhel_vector_dbgprint(const struct vkhel_vector *);

@@ -191,6 +191,39 @@ def test_map_sees_pending_upload_and_kernels(ctx):
     host.free()
 
 
+def test_sliced_pipeline_orders_transfers_per_vector(ctx):
+    """the end-to-end pattern of bench.py: slices rotate through upload ->
+    transforms -> download with no synchronisation in between.  A transfer
+    waits for the last kernel that touched ITS vector (and the previous
+    transfer of it), not for the whole compute stream -- the result must
+    still be exact when buffers are reused many times."""
+    n, batch, nslices, rounds = 1 << 12, 8, 3, 6
+    tp = TablePair(n, params.P0)
+    count = n * batch
+    rng = np.random.default_rng(77)
+    hin = vk.host_alloc(count * nslices * rounds)
+    hout = vk.host_alloc(count * nslices * rounds)
+    hin.array[:] = rand_mod(rng, hin.array.size, tp.q)
+    hout.array[:] = 0
+    slices = [ctx.vector(count, zero=False) for _ in range(nslices)]
+    big = ctx.vector(1 << 22, zero=False)       # unrelated long-running work
+    tbig = TablePair(1 << 16, params.P0)
+    for r in range(rounds):
+        for c, v in enumerate(slices):
+            off = (r * nslices + c) * count
+            v.upload(hin, count=count, host_offset=off)
+            ctx.forward_transform_batch(v, v, tp.lib, batch)
+            ctx.forward_transform_batch(big, big, tbig.lib, 64)
+            v.download(hout, count=count, host_offset=off)
+    ctx.sync()
+    want = oracle.forward_batch(hin.array, [tp.ora], threads=8)
+    assert np.array_equal(hout.array, want)
+    for v in slices + [big]:
+        v.destroy()
+    tp.destroy(), tbig.destroy()
+    hin.free(), hout.free()
+
+
 def test_dbgprint_symbols(ctx, capfd):
     lib = vk.lib()
     v = ctx.from_host(u64([1, 2, 3]))

@@ -3,8 +3,9 @@
 By default q < 2^64/6 runs the approximate-quotient butterflies, larger
 q < 2^62 the exact-quotient ones and q >= 2^62 (or n < 8) the generic kernel.
 The environment switches $VKHEL_EXACT_QUOTIENT and $VKHEL_FORCE_GENERIC force
-the slower families for every modulus; they are read once per process, so the
-parity tests are re-run in child processes."""
+the slower families for every modulus, $VKHEL_POLYMUL_UNFUSED the polynomial
+product as separate transforms; they are read once per process, so the parity
+tests are re-run in child processes."""
 import os
 import subprocess
 import sys
@@ -20,7 +21,8 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
 
 
 @pytest.mark.parametrize("switch", ["VKHEL_EXACT_QUOTIENT",
-                                    "VKHEL_FORCE_GENERIC"])
+                                    "VKHEL_FORCE_GENERIC",
+                                    "VKHEL_POLYMUL_UNFUSED"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)
     env[switch] = "1"

@@ -369,11 +369,13 @@ def test_rns_matches_oracle(ctx, log2n, limbs, batch):
         t.destroy()
 
 
-@pytest.mark.parametrize("log2n,limbs,batch", [(5, 2, 3), (8, 1, 4),
-                                                (12, 3, 2)])
+@pytest.mark.parametrize("log2n,limbs,batch", [(3, 2, 9), (5, 2, 3), (8, 1, 4),
+                                                (9, 2, 5), (12, 3, 2),
+                                                (16, 2, 3), (19, 1, 2)])
 def test_polymul_matches_schoolbook_and_oracle(ctx, log2n, limbs, batch):
     n = 1 << log2n
-    primes = params.ntt_primes(limbs)
+    # n > 2^17 needs more 2-adicity than the RNS primes have
+    primes = params.ntt_primes(limbs) if log2n <= 17 else [params.Q61]
     tps = [TablePair(n, q) for q in primes]
     rng = np.random.default_rng(n)
     polys = limbs * batch
@@ -395,6 +397,37 @@ def test_polymul_matches_schoolbook_and_oracle(ctx, log2n, limbs, batch):
                 got[sl], oracle.negacyclic_schoolbook(a[sl], b[sl], t.q))
     assert np.array_equal(va.to_host(), a) and np.array_equal(vb.to_host(), b)
     va.destroy(), vb.destroy(), vc.destroy()
+    for t in tps:
+        t.destroy()
+
+
+@pytest.mark.parametrize("log2n", [6, 13])
+@pytest.mark.parametrize("alias", ["a", "b", "square"])
+def test_polymul_result_may_alias_operands(ctx, log2n, alias):
+    """result == a, result == b, and a == b == result (in-place squaring)"""
+    n, limbs, batch = 1 << log2n, 2, 3
+    primes = params.ntt_primes(limbs)
+    tps = [TablePair(n, q) for q in primes]
+    rng = np.random.default_rng(log2n)
+    polys = limbs * batch
+    a = np.concatenate([rand_mod(rng, n, primes[p % limbs])
+                        for p in range(polys)])
+    b = a if alias == "square" else np.concatenate(
+        [rand_mod(rng, n, primes[p % limbs]) for p in range(polys)])
+    va = ctx.from_host(a)
+    vb = va if alias == "square" else ctx.from_host(b)
+    vc = vb if alias == "b" else va
+    ctx.polymul_rns(va, vb, vc, [t.lib for t in tps], batch)
+    got = vc.to_host()
+    for p in range(polys):
+        t = tps[p % limbs]
+        sl = slice(p * n, (p + 1) * n)
+        prod = oracle.elemmul(oracle.forward(a[sl], t.ora),
+                              oracle.forward(b[sl], t.ora), t.q)
+        assert np.array_equal(got[sl], oracle.inverse(prod, t.ora)), p
+    va.destroy()
+    if vb is not va:
+        vb.destroy()
     for t in tps:
         t.destroy()
 

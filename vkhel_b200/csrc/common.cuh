@@ -94,4 +94,12 @@ bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max);
 
+/* c = INTT(NTT(a) (*) NTT(b)) per polynomial with the row passes of the three
+ * transforms and the product in one kernel; tmp holds polys << log2n words
+ * (unused for n <= 256).  dst may alias a and/or b.  Returns false when the
+ * fast path does not apply (nothing has been launched then). */
+bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *tmp, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max);
+
 #endif

@@ -93,6 +93,11 @@ extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
 	cudaEvent_t fork_event;
 	CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
 	dev->ev_scratch = fork_event;
+	for (int i = 0; i < VKHEL_FORK_EVENTS; i++) {
+		CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+		dev->fork_ev[i] = fork_event;
+		dev->fork_serial[i] = 0;
+	}
 
 	cudaMemPoolProps props;
 	memset(&props, 0, sizeof(props));
@@ -119,6 +124,9 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_d2h));
 	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_scratch));
+	for (int i = 0; i < VKHEL_FORK_EVENTS; i++) {
+		CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->fork_ev[i]));
+	}
 
 	plan_cache *cache = (plan_cache *) dev->plan_cache;
 	for (rns_plan &plan : cache->plans) {

@@ -631,6 +631,180 @@ ntt_rows_kernel(const fast_pass p) {
 	}
 }
 
+/* ---- fused negacyclic product: the middle of c = INTT(NTT(a) (*) NTT(b)) -------------
+ * The last K stages of the forward transform and the first K stages of the
+ * inverse transform work on the same 2^K contiguous coefficients, so for the
+ * reference's call sequence forward, forward, elemmul, inverse
+ * (src/vector.c:388-427,513-657) the row passes of both forward transforms, the
+ * point-wise product and the row pass of the inverse transform are one kernel:
+ * a tile of a and the matching tile of b are transformed in registers,
+ * multiplied, and taken through the inverse stages before anything is stored.
+ * Against the separate passes this saves the write + read of NTT(a), NTT(b)
+ * and of the product (4 of the 13 vector sweeps of the unfused sequence). */
+template <bool INV, int K, bool FOLD, bool APX>
+__device__ __forceinline__ void rows_rounds(u64 (&x)[1][8], u64 *xb, int t,
+		const ulonglong2 *twt, u64 q, u64 bq, ulonglong2 fold_a,
+		ulonglong2 fold_b) {
+	using G = tile_geom<K>;
+#pragma unroll
+	for (int rr = 0; rr < G::rounds; rr++) {
+		const int r = INV ? G::rounds - 1 - rr : rr;
+		if (rr > 0) {
+			const int prev = INV ? r + 1 : r - 1;
+			u64 *xw = xb + xpad(G::tbase(prev, t));
+			if (G::eoff(prev, 1) == 1) {
+#pragma unroll
+				for (int e = 0; e < 8; e += 2) {
+					*(ulonglong2 *) (xw + xpad(G::eoff(prev, e))) =
+						make_ulonglong2(x[0][e], x[0][e + 1]);
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					xw[xpad(G::eoff(prev, e))] = x[0][e];
+				}
+			}
+			__syncwarp();
+			const u64 *xr = xb + xpad(G::tbase(r, t));
+			if (G::eoff(r, 1) == 1) {
+#pragma unroll
+				for (int e = 0; e < 8; e += 2) {
+					const ulonglong2 v =
+						*(const ulonglong2 *) (xr + xpad(G::eoff(r, e)));
+					x[0][e] = v.x;
+					x[0][e + 1] = v.y;
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 8; e++) {
+					x[0][e] = xr[xpad(G::eoff(r, e))];
+				}
+			}
+		}
+		tile_round<K, INV, FOLD, 1, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
+	}
+}
+
+#ifndef PMUL_MIN_CTAS
+#define PMUL_MIN_CTAS 4
+#endif
+
+template <int K, bool APX>
+__global__ void __launch_bounds__(FAST_THREADS, PMUL_MIN_CTAS)
+ntt_rows_polymul_kernel(const fast_pass p) {
+	using G = tile_geom<K>;
+	using C = row_cfg<K>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	const unsigned L = p.log2n, s0 = p.s0;       /* s0 + K == L */
+	const unsigned hgroup = 1u << p.hgroup_log2;
+	ulonglong2 *sm_twf = (ulonglong2 *) smem_raw;                /* [hgroup][2^K] */
+	ulonglong2 *sm_twi = sm_twf + ((size_t) hgroup << K);        /* [hgroup][2^K] */
+	u64 *sm_x = (u64 *) (sm_twi + ((size_t) hgroup << K));       /* per group */
+
+	const unsigned hgroups = (1u << s0) >> p.hgroup_log2;
+	unsigned blk = blockIdx.x;
+	const unsigned hg = blk % hgroups;
+	blk /= hgroups;
+	const unsigned limb = blk % p.limbs;
+	const unsigned bc = blk / p.limbs;
+	const u64 batch = p.polys / p.limbs;
+	const u64 b0 = (u64) bc * p.bchunk;
+	const unsigned nb = (unsigned) (batch - b0 < p.bchunk ? batch - b0 : p.bchunk);
+	const unsigned H0 = hg << p.hgroup_log2;
+
+	const limb_desc &d = p.descs[limb];
+	const u64 q = d.q, bq = APX ? 3 * q : 2 * q;
+	__shared__ __align__(8) u64 tw_bar[2];
+	if (threadIdx.x == 0) {
+		mbar_init(&tw_bar[0], 1);
+		mbar_init(&tw_bar[1], 1);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		stage_twiddles_tma<K>(sm_twf, d.tw, s0, H0, hgroup, &tw_bar[0]);
+		stage_twiddles_tma<K>(sm_twi, d.tw + ((u64) 1 << L), s0, H0, hgroup,
+				&tw_bar[1]);
+	}
+	bool tw_ready = false;
+	pdl_wait();   /* the coefficients come from the previous kernels */
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int t = lane & (C::group - 1);
+	const int slot = warp * C::groups_per_warp + (lane >> (K - 3));
+	u64 *xb = sm_x + (size_t) slot * C::xbuf;
+	const bool fold = s0 == 0;          /* single pass: the whole product here */
+	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
+	if (fold) {
+		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+		fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
+	}
+	modulus m;
+	m.q = q;
+	m.d = d.mm_d;
+	m.v = d.mm_v;
+	m.s = d.mm_s;
+	m.mu = 0;
+	/* both directions enter and leave in the layout of round 0 */
+	const int tb0 = G::tbase(0, t);
+
+	const unsigned nitems = nb << p.hgroup_log2;
+	for (unsigned base = 0; base < nitems; base += C::groups_per_cta) {
+		const unsigned idx = base + slot;
+		const unsigned h = idx & (hgroup - 1), bl = idx >> p.hgroup_log2;
+		const bool active = idx < nitems;
+		const u64 poly = (b0 + bl) * p.limbs + limb;
+		const u64 off = (poly << L) + ((u64) (H0 + h) << K) + tb0;
+		const ulonglong2 *twf = sm_twf + ((size_t) h << K);
+		const ulonglong2 *twi = sm_twi + ((size_t) h << K);
+		u64 xa[1][8], x[1][8];
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			xa[0][e] = active ? p.src[off + G::eoff(0, e)] : 0;
+		}
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			x[0][e] = active ? p.src2[off + G::eoff(0, e)] : 0;
+		}
+		if (!tw_ready) {
+			mbar_wait(&tw_bar[0], 0);
+			mbar_wait(&tw_bar[1], 0);
+			tw_ready = true;
+		}
+		rows_rounds<false, K, false, APX>(xa, xb, t, twf, q, bq, fold_a, fold_b);
+		__syncwarp();   /* the exchange buffer changes hands */
+		rows_rounds<false, K, false, APX>(x, xb, t, twf, q, bq, fold_a, fold_b);
+		/* point-wise product (reference elemmul.comp:62-73): one factor is
+		 * made canonical, the other stays lazy (below 2*bq), so the high word
+		 * of the product is below q as reduce128 requires; the result is the
+		 * canonical residue the reference's elemmul would have stored */
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			const u64 ca = tile_canon<false, APX>(xa[0][e], q, bq);
+			x[0][e] = mulmod(ca, x[0][e], m);
+		}
+		if (fold) {
+			rows_rounds<true, K, true, APX>(x, xb, t, twi, q, bq, fold_a, fold_b);
+		} else {
+			rows_rounds<true, K, false, APX>(x, xb, t, twi, q, bq, fold_a, fold_b);
+		}
+		__syncwarp();   /* the exchange buffer is reused by the next item */
+		if (base + C::groups_per_cta >= nitems) {
+			pdl_launch_dependents();
+		}
+		if (active) {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				u64 v = x[0][e];
+				if (fold) {
+					v = tile_canon<true, APX>(v, q, bq);
+				}
+				p.dst[off + G::eoff(0, e)] = v;
+			}
+		}
+	}
+}
+
 /* Column pass.  CTA = (poly, H, column group): one tile group of 2^K rows at
  * stride 2^(L-s0-K) by 2^CL adjacent columns.  thread = (row group, NP adjacent
  * columns), lanes along the columns: every global access is a run of 2^CL * 8
@@ -982,6 +1156,120 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	}
 }
 
+template <int K, bool APX>
+static void run_rows_polymul(struct vkhel_ctx *ctx, fast_pass p) {
+	using C = row_cfg<K>;
+	const u64 batch = p.polys / p.limbs;
+	unsigned hgroup_log2 = 0;
+	while ((1u << hgroup_log2) < (unsigned) C::groups_per_cta
+			&& hgroup_log2 < p.s0
+			&& (batch << hgroup_log2) < (u64) C::groups_per_cta) {
+		hgroup_log2++;
+	}
+	u64 bchunk = (ROWS_ROUNDS_PER_CTA * (u64) C::groups_per_cta) >> hgroup_log2;
+	if (bchunk < 1) {
+		bchunk = 1;
+	}
+	if (bchunk > batch) {
+		bchunk = batch;
+	}
+	p.hgroup_log2 = hgroup_log2;
+	p.bchunk = (unsigned) bchunk;
+	const u64 bchunks = (batch + bchunk - 1) / bchunk;
+	const u64 blocks = bchunks * p.limbs * ((1ull << p.s0) >> hgroup_log2);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "product too large for one launch");
+	const size_t smem = 2 * ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
+		+ (size_t) C::groups_per_cta * C::xbuf * sizeof(u64);
+	if (smem > 48 * 1024) {
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_polymul_kernel<K, APX>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
+	launch_fast(ctx, ntt_rows_polymul_kernel<K, APX>, (unsigned) blocks,
+			FAST_THREADS, smem, p);
+}
+
+template <bool APX>
+static void run_rows_polymul_k(struct vkhel_ctx *ctx, const fast_pass &p,
+		unsigned k) {
+	switch (k) {
+	case 3: run_rows_polymul<3, APX>(ctx, p); break;
+	case 4: run_rows_polymul<4, APX>(ctx, p); break;
+	case 5: run_rows_polymul<5, APX>(ctx, p); break;
+	case 6: run_rows_polymul<6, APX>(ctx, p); break;
+	case 7: run_rows_polymul<7, APX>(ctx, p); break;
+	case 8: run_rows_polymul<8, APX>(ctx, p); break;
+	default: VK_DIE("internal: row pass of %u stages", k);
+	}
+}
+
+/* c = INTT(NTT(a) (*) NTT(b)): the strided passes of both forward transforms
+ * (b into tmp first, so that dst may alias a, b or both), the fused middle
+ * kernel, the strided passes of the inverse.  n <= 256: the middle kernel is
+ * the whole product and tmp is not used. */
+template <bool APX>
+static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *tmp, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n) {
+	const fast_plan pl = plan_fast(log2n);
+	fast_pass p;
+	p.src2 = NULL;
+	p.descs = descs;
+	p.limbs = (unsigned) limbs;
+	p.log2n = log2n;
+	p.polys = polys;
+	p.hgroup_log2 = 0;
+	p.bchunk = 1;
+
+	gen_pass lead;
+	lead.descs = descs;
+	lead.limbs = (unsigned) limbs;
+	lead.log2n = log2n;
+	lead.s0 = 0;
+	lead.k = pl.lead;
+	lead.tiles = polys;
+	lead.last = false;
+
+	const u64 *cur_a = a, *cur_b = b;
+	if (pl.lead) {
+		lead.src = b;
+		lead.dst = tmp;
+		run_generic_pass<false, false>(ctx, lead);
+		lead.src = a;
+		lead.dst = dst;
+		run_generic_pass<false, false>(ctx, lead);
+		cur_a = dst;
+		cur_b = tmp;
+	}
+	if (pl.kcol) {
+		p.s0 = pl.lead;
+		p.src = cur_b;
+		p.dst = tmp;
+		run_cols_k<false, APX>(ctx, p, pl.kcol);
+		p.src = cur_a;
+		p.dst = dst;
+		run_cols_k<false, APX>(ctx, p, pl.kcol);
+		cur_a = dst;
+		cur_b = tmp;
+	}
+	p.src = cur_a;
+	p.src2 = cur_b;
+	p.dst = dst;
+	p.s0 = pl.lead + pl.kcol;
+	run_rows_polymul_k<APX>(ctx, p, pl.krow);
+	p.src2 = NULL;
+	if (pl.kcol) {
+		p.src = dst;
+		p.s0 = pl.lead;
+		run_cols_k<true, APX>(ctx, p, pl.kcol);
+	}
+	if (pl.lead) {
+		lead.src = dst;
+		lead.dst = dst;
+		lead.last = true;
+		run_generic_pass<true, false>(ctx, lead);
+	}
+}
+
 /* ======================================================================================
  * Dispatch
  * ====================================================================================== */
@@ -1033,6 +1321,22 @@ bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n, src2);
 	} else {
 		run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+	}
+	return true;
+}
+
+bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
+		u64 *tmp, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max) {
+	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
+	static const bool unfused = getenv("VKHEL_POLYMUL_UNFUSED") != NULL;
+	if (q_max >= (1ull << 62) || log2n < 3 || force_generic || unfused) {
+		return false;
+	}
+	if (use_approx(q_max, log2n)) {
+		run_fast_polymul<true>(ctx, a, b, tmp, dst, descs, limbs, polys, log2n);
+	} else {
+		run_fast_polymul<false>(ctx, a, b, tmp, dst, descs, limbs, polys, log2n);
 	}
 	return true;
 }

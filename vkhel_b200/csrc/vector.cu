@@ -22,21 +22,47 @@ static void enter(const struct vkhel_ctx *ctx) {
  * asynchronous upload/download of this vector is still in flight on a copy
  * stream, the compute stream is made to wait for it first (once). */
 static inline u64 *dev_u64(const struct vkhel_vector *v) {
+	struct vkhel_vector *vec = (struct vkhel_vector *) v;
 	if (v->xfer_pending) {
-		struct vkhel_vector *vec = (struct vkhel_vector *) v;
 		CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(vec->ctx),
 					(cudaEvent_t) vec->xfer_event, 0));
 		vec->xfer_pending = 0;
 	}
+	vec->last_op = ++vec->ctx->dev.op_serial;
 	return (u64 *) v->device.ptr;
 }
 
-/* start a transfer of `vec` on copy stream `copy`: it must come after all
- * compute enqueued so far and after the previous transfer of this vector */
+/* An event on the compute stream that covers every operation up to serial
+ * number `serial`: the oldest recorded one that does, or a new one. */
+static cudaEvent_t fork_event_covering(struct vkhel_ctx *ctx, uint64_t serial,
+		bool fresh) {
+	struct device_ctx *dev = &ctx->dev;
+	int best = -1;
+	for (int i = 0; i < VKHEL_FORK_EVENTS && !fresh; i++) {
+		if (dev->fork_serial[i] >= serial && dev->fork_serial[i] != 0
+				&& (best < 0 || dev->fork_serial[i] < dev->fork_serial[best])) {
+			best = i;
+		}
+	}
+	if (best < 0) {
+		best = dev->fork_next;
+		dev->fork_next = (best + 1) % VKHEL_FORK_EVENTS;
+		CUDA_CHECK(cudaEventRecord((cudaEvent_t) dev->fork_ev[best],
+					ctx_stream(ctx)));
+		/* serial 0 marks an unused slot */
+		dev->fork_serial[best] = dev->op_serial ? dev->op_serial
+			: ++dev->op_serial;
+	}
+	return (cudaEvent_t) dev->fork_ev[best];
+}
+
+/* start a transfer of `vec` on copy stream `copy`: it must come after the
+ * last operation on the compute stream that touched the vector (not after
+ * unrelated kernels enqueued since: the upload of the next slice overlaps the
+ * transform of this one) and after the previous transfer of this vector */
 static void xfer_begin(struct vkhel_vector *vec, cudaStream_t copy) {
 	struct vkhel_ctx *ctx = vec->ctx;
-	cudaEvent_t fork = (cudaEvent_t) ctx->dev.ev_scratch;
-	CUDA_CHECK(cudaEventRecord(fork, ctx_stream(ctx)));
+	cudaEvent_t fork = fork_event_covering(ctx, vec->last_op, vec->exposed);
 	CUDA_CHECK(cudaStreamWaitEvent(copy, fork, 0));
 	if (!vec->xfer_event) {
 		cudaEvent_t ev;
@@ -68,6 +94,9 @@ extern "C" struct vkhel_vector *vkhel_vector_create2(struct vkhel_ctx *ctx,
 		CUDA_CHECK(cudaMemsetAsync(vec->device.ptr, 0, vec->device.bytes,
 					ctx_stream(ctx)));
 	}
+	/* the block may come from a stream-ordered free that is still pending
+	 * on the compute stream; count the allocation as a use */
+	vec->last_op = ++ctx->dev.op_serial;
 	return vec;
 }
 
@@ -101,7 +130,7 @@ extern "C" struct vkhel_vector *vkhel_vector_dup(struct vkhel_vector *src) {
 	struct vkhel_vector *dup = vkhel_vector_create2(src->ctx, src->length,
 			false);
 	if (src->length) {
-		CUDA_CHECK(cudaMemcpyAsync(dup->device.ptr, dev_u64(src),
+		CUDA_CHECK(cudaMemcpyAsync(dev_u64(dup), dev_u64(src),
 					src->device.bytes, cudaMemcpyDeviceToDevice,
 					ctx_stream(src->ctx)));
 	}
@@ -175,6 +204,9 @@ extern "C" uint64_t vkhel_vector_length(const struct vkhel_vector *vec) {
 }
 
 extern "C" void *vkhel_vector_device_ptr(struct vkhel_vector *vec) {
+	/* the caller may enqueue its own kernels on vkhel_ctx_stream(): from now
+	 * on transfers of this vector wait for the whole compute stream */
+	vec->exposed = 1;
 	return dev_u64(vec);
 }
 
@@ -488,25 +520,31 @@ extern "C" void vkhel_vector_polymul_rns(
 	if (batch == 0) {
 		return;
 	}
-	/* the reference API sequence NTT(a) -> result, NTT(b) -> scratch,
-	 * product, inverse -- with the product folded into the inverse */
 	u64 *tmp = (u64 *) device_scratch(ctx, total * sizeof(u64));
+	const unsigned log2n = (unsigned) ntt[0]->log2n;
+	const u64 *pa = dev_u64(a), *pb = dev_u64(b);
+	u64 *pr = dev_u64(result);
+	/* fast path: strided passes of NTT(b) -> scratch and NTT(a) -> result,
+	 * then one kernel for the row passes of both, the product and the row
+	 * pass of the inverse, then the strided passes of the inverse */
+	if (launch_ntt_polymul(ctx, pa, pb, tmp, pr, descs, limbs, limbs * batch,
+				log2n, q_max)) {
+		return;
+	}
+	/* otherwise the reference API sequence, NTT(b) first so that result may
+	 * alias either operand: NTT(b) -> scratch, NTT(a) -> result, product
+	 * (folded into the first pass of the inverse where that kernel applies),
+	 * inverse */
 	uint64_t mods[64];
 	for (uint64_t l = 0; l < limbs; l++) {
 		mods[l] = ntt[l]->q;
 	}
-	const unsigned log2n = (unsigned) ntt[0]->log2n;
-	launch_ntt(ctx, false, dev_u64(a), dev_u64(result), descs, limbs,
-			limbs * batch, log2n, q_max);
-	launch_ntt(ctx, false, dev_u64(b), tmp, descs, limbs, limbs * batch,
-			log2n, q_max);
-	/* point-wise product fused into the first pass of the inverse transform
-	 * where the fast path applies; otherwise the separate element-wise kernel */
-	if (!launch_ntt_inverse_of_product(ctx, dev_u64(result), tmp,
-				dev_u64(result), descs, limbs, limbs * batch, log2n, q_max)) {
-		launch_elemmul_rns(ctx, dev_u64(result), tmp, dev_u64(result), mods,
-				limbs, n, batch);
-		launch_ntt(ctx, true, dev_u64(result), dev_u64(result), descs, limbs,
-				limbs * batch, log2n, q_max);
+	launch_ntt(ctx, false, pb, tmp, descs, limbs, limbs * batch, log2n, q_max);
+	launch_ntt(ctx, false, pa, pr, descs, limbs, limbs * batch, log2n, q_max);
+	if (!launch_ntt_inverse_of_product(ctx, pr, tmp, pr, descs, limbs,
+				limbs * batch, log2n, q_max)) {
+		launch_elemmul_rns(ctx, pr, tmp, pr, mods, limbs, n, batch);
+		launch_ntt(ctx, true, pr, pr, descs, limbs, limbs * batch, log2n,
+				q_max);
 	}
 }
