@@ -48,6 +48,9 @@ struct device_ctx {
 	void *scratch;       /* transform scratch (two-pass out-of-place) */
 	size_t scratch_bytes;
 	uint64_t launches;   /* kernels launched so far */
+	void *defer;         /* recorded single-vector transforms (opaque, C++) */
+	uint64_t deferred_batches;    /* indirect batches launched so far */
+	uint64_t deferred_transforms; /* transforms that went out in them */
 };
 
 void device_ctx_init(struct device_ctx *dev, int device);

@@ -96,6 +96,16 @@ void vkhel_timer_destroy(struct vkhel_timer *);
 
 /* number of kernels this context has launched so far */
 uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *);
+/* vkhel_vector_forward_transform / _inverse_transform (one vector per call,
+ * reference src/vector.c:513-657) are recorded and consecutive independent
+ * calls with the same tables go out as one batched launch when the context is
+ * next needed (see vector.cu).  These report how many such batches were
+ * launched and how many transforms they carried; vkhel_ctx_flush launches
+ * what is recorded without waiting for it.  $VKHEL_NO_DEFER=1 disables
+ * recording. */
+void vkhel_ctx_deferred_stats(const struct vkhel_ctx *, uint64_t *batches,
+		uint64_t *transforms);
+void vkhel_ctx_flush(struct vkhel_ctx *);
 /* write a buffer larger than L2 so the next kernel starts cold */
 void vkhel_ctx_flush_l2(struct vkhel_ctx *);
 

@@ -1,0 +1,185 @@
+"""GPU suite: the reference's one-vector-per-call transforms
+(vkhel_vector_forward_transform / _inverse_transform, src/vector.c:513-657)
+are recorded and launched as indirect batches (vkhel_b200/csrc/vector.cu).
+Whatever the call pattern, the results must be those of immediate launches:
+every case is checked against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle
+import vkhel_b200 as vk
+from vkhel_b200 import params
+from conftest import rand_mod
+
+pytestmark = pytest.mark.gpu
+
+
+class Tables:
+    def __init__(self, n, q):
+        self.n, self.q = n, q
+        self.w = params.find_psi(n, q)
+        self.lib = vk.NttTables(n, q, self.w)
+        self.ora = oracle.Tables(n, q, self.w)
+
+    def destroy(self):
+        self.lib.destroy()
+
+
+@pytest.mark.parametrize("log2n,count", [(3, 40), (8, 33), (9, 17), (12, 64),
+                                         (16, 5)])
+def test_loop_over_vectors_is_one_batch(ctx, log2n, count):
+    n = 1 << log2n
+    t = Tables(n, params.P0)
+    rng = np.random.default_rng(log2n)
+    xs = [rand_mod(rng, n, t.q) for _ in range(count)]
+    vs = [ctx.from_host(x) for x in xs]
+    outs = [ctx.vector(n, zero=False) for _ in range(count)]
+    ctx.sync()
+    b0, t0 = ctx.deferred_stats
+    for v, o in zip(vs, outs):
+        ctx.forward_transform(v, o, t.lib)
+    for o in outs:                      # in place, other direction: new batch
+        ctx.inverse_transform(o, o, t.lib)
+    for v in vs:                        # in place forward
+        ctx.forward_transform(v, v, t.lib)
+    ctx.sync()
+    b1, t1 = ctx.deferred_stats
+    assert (b1 - b0, t1 - t0) == (3, 3 * count)
+    for x, v, o in zip(xs, vs, outs):
+        assert np.array_equal(o.to_host(), x)
+        assert np.array_equal(v.to_host(), oracle.forward(x, t.ora))
+    for v in vs + outs:
+        v.destroy()
+    t.destroy()
+
+
+def test_dependent_transforms_are_not_reordered(ctx):
+    n = 1 << 10
+    t = Tables(n, params.P0)
+    rng = np.random.default_rng(1)
+    x, y = rand_mod(rng, n, t.q), rand_mod(rng, n, t.q)
+    a, b, c = ctx.from_host(x), ctx.vector(n), ctx.from_host(y)
+    ctx.forward_transform(a, b, t.lib)      # b = F(x)
+    ctx.forward_transform(b, b, t.lib)      # RAW + WAW on b: b = F(F(x))
+    ctx.forward_transform(c, a, t.lib)      # WAR on a: a = F(y)
+    ctx.forward_transform(a, c, t.lib)      # RAW on a: c = F(F(y))
+    fx, fy = oracle.forward(x, t.ora), oracle.forward(y, t.ora)
+    assert np.array_equal(b.to_host(), oracle.forward(fx, t.ora))
+    assert np.array_equal(a.to_host(), fy)
+    assert np.array_equal(c.to_host(), oracle.forward(fy, t.ora))
+    # the same vector three times in place
+    v = ctx.from_host(x)
+    for _ in range(3):
+        ctx.forward_transform(v, v, t.lib)
+    want = x
+    for _ in range(3):
+        want = oracle.forward(want, t.ora)
+    assert np.array_equal(v.to_host(), want)
+    for vec in (a, b, c, v):
+        vec.destroy()
+    t.destroy()
+
+
+def test_shared_operand_and_mixed_tables(ctx):
+    n1, n2 = 1 << 7, 1 << 11
+    t1, t2 = Tables(n1, params.P0), Tables(n2, params.ntt_primes(2)[1])
+    rng = np.random.default_rng(2)
+    x1, x2 = rand_mod(rng, n1, t1.q), rand_mod(rng, n2, t2.q)
+    a1, a2 = ctx.from_host(x1), ctx.from_host(x2)
+    outs1 = [ctx.vector(n1) for _ in range(4)]
+    outs2 = [ctx.vector(n2) for _ in range(4)]
+    for o1, o2 in zip(outs1, outs2):        # tables alternate: batches of 1
+        ctx.forward_transform(a1, o1, t1.lib)
+        ctx.forward_transform(a2, o2, t2.lib)
+    f1, f2 = oracle.forward(x1, t1.ora), oracle.forward(x2, t2.ora)
+    for o1, o2 in zip(outs1, outs2):
+        assert np.array_equal(o1.to_host(), f1)
+        assert np.array_equal(o2.to_host(), f2)
+    # one operand read by many recorded transforms (no hazard)
+    b0, _ = ctx.deferred_stats
+    for o in outs1:
+        ctx.inverse_transform(a1, o, t1.lib)
+    ctx.flush()
+    assert ctx.deferred_stats[0] == b0 + 1
+    i1 = oracle.inverse(x1, t1.ora)
+    for o in outs1:
+        assert np.array_equal(o.to_host(), i1)
+    for vec in [a1, a2] + outs1 + outs2:
+        vec.destroy()
+    t1.destroy(), t2.destroy()
+
+
+def test_recorded_transforms_meet_other_operations(ctx):
+    """element-wise ops, transfers, dup, destroy of vectors and of the tables
+    while transforms are still only recorded"""
+    n = 1 << 9
+    t = Tables(n, params.P0)
+    q = t.q
+    rng = np.random.default_rng(3)
+    xs = [rand_mod(rng, n, q) for _ in range(6)]
+    vs = [ctx.from_host(x) for x in xs]
+    fs = [oracle.forward(x, t.ora) for x in xs]
+    for v in vs:
+        ctx.forward_transform(v, v, t.lib)
+    prod = ctx.vector(n)
+    ctx.elemmul(vs[0], vs[1], prod, q)           # element-wise right after
+    assert np.array_equal(prod.to_host(), oracle.elemmul(fs[0], fs[1], q))
+    for v in vs:
+        ctx.inverse_transform(v, v, t.lib)
+    d = vs[2].dup()                              # dup sees the transform
+    assert np.array_equal(d.to_host(), xs[2])
+    # download / upload of a vector with a recorded transform
+    host = vk.host_alloc(n)
+    ctx.forward_transform(vs[3], vs[3], t.lib)
+    vs[3].download(host)
+    ctx.sync()
+    assert np.array_equal(host.array, fs[3])
+    ctx.forward_transform(vs[4], vs[4], t.lib)
+    host.array[:] = xs[5]
+    vs[4].upload(host)                           # overwrites the result
+    ctx.forward_transform(vs[4], vs[4], t.lib)
+    assert np.array_equal(vs[4].to_host(), fs[5])
+    # destroy a vector, then the tables, with transforms recorded
+    out = ctx.vector(n)
+    ctx.forward_transform(vs[0], out, t.lib)
+    tmp = ctx.from_host(xs[1])
+    ctx.forward_transform(tmp, tmp, t.lib)
+    tmp.destroy()
+    t.destroy()
+    assert np.array_equal(out.to_host(), fs[0])
+    for vec in vs + [prod, d, out]:
+        vec.destroy()
+    host.free()
+
+
+def test_more_vectors_than_one_batch_holds(ctx):
+    n, count = 8, 4096 + 700
+    t = Tables(n, params.P0)
+    rng = np.random.default_rng(4)
+    x = rand_mod(rng, n * count, t.q)
+    vs = [ctx.from_host(x[i * n:(i + 1) * n]) for i in range(count)]
+    for v in vs:
+        ctx.forward_transform(v, v, t.lib)
+    want = oracle.forward_batch(x, [t.ora], threads=8)
+    got = np.concatenate([v.to_host() for v in vs])
+    assert np.array_equal(got, want)
+    for v in vs:
+        v.destroy()
+    t.destroy()
+
+
+def test_inverse_with_tail_and_unsupported_moduli_bypass_the_queue(ctx):
+    n = 64
+    t = Tables(n, params.P0)
+    ts = Tables(n, params.Q63_STRICT)
+    rng = np.random.default_rng(5)
+    x = rand_mod(rng, n + 9, t.q)
+    v = ctx.from_host(x)
+    ctx.inverse_transform(v, v, t.lib)           # result longer than n
+    want = oracle.inverse(x[:n], t.ora, out_len=n + 9, out_init=x)
+    assert np.array_equal(v.to_host(), want)
+    y = rand_mod(rng, n, ts.q)
+    w = ctx.from_host(y)
+    ctx.forward_transform(w, w, ts.lib)          # strict path, 63-bit modulus
+    assert np.array_equal(w.to_host(), oracle.forward(y, ts.ora))
+    v.destroy(), w.destroy(), t.destroy(), ts.destroy()

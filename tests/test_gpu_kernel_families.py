@@ -22,7 +22,8 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
 
 @pytest.mark.parametrize("switch", ["VKHEL_EXACT_QUOTIENT",
                                     "VKHEL_FORCE_GENERIC",
-                                    "VKHEL_POLYMUL_UNFUSED"])
+                                    "VKHEL_POLYMUL_UNFUSED",
+                                    "VKHEL_NO_DEFER"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)
     env[switch] = "1"

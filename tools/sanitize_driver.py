@@ -47,6 +47,28 @@ def main():
     ctx.forward_transform(v, v, t)
     ctx.inverse_transform(v, v, t)
     v.to_host()
+    # recorded one-vector transforms going out as indirect batches, and the
+    # fused polynomial product
+    for log2n in (5, 9, 13):
+        n, q = 1 << log2n, params.P0
+        t2 = vk.NttTables(n, q, params.find_psi(n, q))
+        o2 = oracle.Tables(n, q, t2.w)
+        xs = [rng.integers(0, q, n, dtype=np.uint64) for _ in range(5)]
+        vs = [ctx.from_host(x) for x in xs]
+        for vec in vs:
+            ctx.forward_transform(vec, vec, t2)
+        for x, vec in zip(xs, vs):
+            assert np.array_equal(vec.to_host(), oracle.forward(x, o2))
+        for vec in vs:
+            ctx.inverse_transform(vec, vec, t2)
+        assert np.array_equal(vs[4].to_host(), xs[4])
+        ctx.polymul_rns(vs[0], vs[1], vs[2], [t2], 1)
+        prod = oracle.elemmul(oracle.forward(xs[0], o2),
+                              oracle.forward(xs[1], o2), q)
+        assert np.array_equal(vs[2].to_host(), oracle.inverse(prod, o2))
+        for vec in vs:
+            vec.destroy()
+        t2.destroy()
     q = 769
     a = ctx.from_host(rng.integers(0, 1 << 62, 1001, dtype=np.uint64))
     c = ctx.vector(1001)

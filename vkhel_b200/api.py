@@ -79,6 +79,8 @@ SIGNATURES = {
     "vkhel_timer_destroy": (None, [_vp]),
     "vkhel_ctx_launch_count": (_u64, [_vp]),
     "vkhel_ctx_flush_l2": (None, [_vp]),
+    "vkhel_ctx_flush": (None, [_vp]),
+    "vkhel_ctx_deferred_stats": (None, [_vp, _p64, _p64]),
 }
 
 _lib = None
@@ -234,6 +236,18 @@ class Context:
 
     def flush_l2(self):
         lib().vkhel_ctx_flush_l2(self.handle)
+
+    def flush(self):
+        """launch the recorded single-vector transforms (no wait)"""
+        lib().vkhel_ctx_flush(self.handle)
+
+    @property
+    def deferred_stats(self):
+        """(batched launches, transforms carried by them) so far"""
+        b, t = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        lib().vkhel_ctx_deferred_stats(self.handle, ctypes.byref(b),
+                                       ctypes.byref(t))
+        return int(b.value), int(t.value)
 
     @property
     def launch_count(self):

@@ -50,6 +50,13 @@ struct limb_desc {
 	unsigned mm_s, pad_[3];
 };
 
+/* one polynomial of an indirect batch (deferred single-vector transforms that
+ * are launched together, vector.cu) */
+struct ntt_ptrs {
+	const u64 *src;
+	u64 *dst;
+};
+
 /* device.cu */
 extern "C" void *device_alloc(struct vkhel_ctx *ctx, size_t bytes);
 extern "C" void device_free(struct vkhel_ctx *ctx, void *ptr);
@@ -101,5 +108,20 @@ bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		u64 *tmp, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max);
+
+/* the same transform on `polys` separate polynomials of one table, polynomial
+ * i read from tab[i].src and written to tab[i].dst (tab in device memory);
+ * only where ntt_indirect_supported() */
+bool ntt_indirect_supported(unsigned log2n, uint64_t q);
+void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
+		const ntt_ptrs *tab, const limb_desc *desc, uint64_t polys,
+		unsigned log2n, uint64_t q);
+
+/* vector.cu: launch the deferred single-vector transforms of the context (all
+ * of them, or only if they use `ntt`) */
+void defer_flush(struct vkhel_ctx *ctx);
+void defer_flush_tables(struct vkhel_ctx *ctx,
+		const struct vkhel_ntt_tables *ntt);
+void defer_destroy(struct vkhel_ctx *ctx);
 
 #endif

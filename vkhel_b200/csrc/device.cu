@@ -14,6 +14,7 @@
  * op (src/vector.c:327), here only map/dbgprint/destroy/sync wait.
  */
 #include <string.h>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -40,6 +41,27 @@ struct rns_plan {
 struct plan_cache {
 	std::vector<rns_plan> plans;
 };
+
+/* ---- live contexts ----------------------------------------------------------
+ * NTT tables belong to no context, but a context may hold recorded transforms
+ * that use them (vector.cu): destroying tables first launches those. */
+static std::mutex g_registry_lock;
+static std::vector<struct vkhel_ctx *> g_registry;
+
+static void registry_add(struct vkhel_ctx *ctx) {
+	std::lock_guard<std::mutex> guard(g_registry_lock);
+	g_registry.push_back(ctx);
+}
+
+static void registry_remove(struct vkhel_ctx *ctx) {
+	std::lock_guard<std::mutex> guard(g_registry_lock);
+	for (size_t i = 0; i < g_registry.size(); i++) {
+		if (g_registry[i] == ctx) {
+			g_registry.erase(g_registry.begin() + i);
+			break;
+		}
+	}
+}
 
 /* ---- context -------------------------------------------------------------- */
 extern "C" int vkhel_device_count(void) {
@@ -117,6 +139,9 @@ extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
 
 extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	enter_device(dev->device);
+	/* struct vkhel_ctx is exactly its device_ctx (priv/vkhel.h) */
+	defer_destroy((struct vkhel_ctx *) dev);
+	registry_remove((struct vkhel_ctx *) dev);
 	cudaStream_t stream = (cudaStream_t) dev->stream;
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_d2h));
@@ -154,6 +179,7 @@ extern "C" struct vkhel_ctx *vkhel_ctx_create_device(int device) {
 	struct vkhel_ctx *ctx = (struct vkhel_ctx *) calloc(1, sizeof(*ctx));
 	VK_REQUIRE(ctx, "out of host memory");
 	device_ctx_init(&ctx->dev, device);
+	registry_add(ctx);
 	return ctx;
 }
 
@@ -180,21 +206,41 @@ extern "C" int vkhel_ctx_device(const struct vkhel_ctx *ctx) {
 
 extern "C" void vkhel_ctx_sync(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
+	defer_flush(ctx);
 	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) ctx->dev.stream_h2d));
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) ctx->dev.stream_d2h));
 }
 
 extern "C" void *vkhel_ctx_stream(struct vkhel_ctx *ctx) {
+	/* the caller is about to order its own work against ours */
+	defer_flush(ctx);
 	return ctx->dev.stream;
 }
 
 extern "C" uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *ctx) {
+	defer_flush((struct vkhel_ctx *) ctx);
 	return ctx->dev.launches;
+}
+
+extern "C" void vkhel_ctx_deferred_stats(const struct vkhel_ctx *ctx,
+		uint64_t *batches, uint64_t *transforms) {
+	if (batches) {
+		*batches = ctx->dev.deferred_batches;
+	}
+	if (transforms) {
+		*transforms = ctx->dev.deferred_transforms;
+	}
+}
+
+extern "C" void vkhel_ctx_flush(struct vkhel_ctx *ctx) {
+	ctx_enter(ctx);
+	defer_flush(ctx);
 }
 
 extern "C" void vkhel_ctx_flush_l2(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
+	defer_flush(ctx);
 	struct device_ctx *dev = &ctx->dev;
 	if (!dev->flush_buf) {
 		/* twice the L2 so that every line is displaced */
@@ -363,6 +409,12 @@ const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,
 }
 
 extern "C" void ntt_tables_release_device(struct vkhel_ntt_tables *ntt) {
+	{
+		std::lock_guard<std::mutex> guard(g_registry_lock);
+		for (struct vkhel_ctx *ctx : g_registry) {
+			defer_flush_tables(ctx, ntt);
+		}
+	}
 	for (int device = 0; device < VKHEL_MAX_DEVICES; device++) {
 		if (!ntt->dev_pairs[device]) {
 			continue;
@@ -435,11 +487,13 @@ extern "C" struct vkhel_timer *vkhel_timer_create(struct vkhel_ctx *ctx) {
 
 extern "C" void vkhel_timer_start(struct vkhel_timer *timer) {
 	ctx_enter(timer->ctx);
+	defer_flush(timer->ctx);
 	CUDA_CHECK(cudaEventRecord(timer->start, ctx_stream(timer->ctx)));
 }
 
 extern "C" void vkhel_timer_stop(struct vkhel_timer *timer) {
 	ctx_enter(timer->ctx);
+	defer_flush(timer->ctx);
 	/* join the copy streams first, so that the interval covers uploads and
 	 * downloads enqueued since start as well as the kernels */
 	struct device_ctx *dev = &timer->ctx->dev;

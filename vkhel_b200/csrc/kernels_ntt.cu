@@ -297,6 +297,11 @@ struct fast_pass {
 	u64 polys;            /* batch * limbs */
 	unsigned hgroup_log2; /* row pass: consecutive H per CTA */
 	unsigned bchunk;      /* row pass: batch entries per CTA */
+	/* indirect batch (kernels instantiated with IND): polynomial i lives at
+	 * tab[i].src / tab[i].dst instead of src + i*n / dst + i*n; the second
+	 * pass of a transform reads what the first one wrote (tab[i].dst) */
+	const ntt_ptrs *tab;
+	unsigned tab_second;
 };
 
 /* padded position of tile element i in a warp-group's exchange buffer: 4 words
@@ -413,10 +418,11 @@ struct row_cfg {
 /* Row pass.  CTA = (batch chunk, limb, H group): `bchunk` batch entries of
  * 2^hgroup_log2 consecutive tiles sharing one staged twiddle set.  A warp-group
  * of 2^(K-3) lanes carries NP batch entries of one tile position at a time. */
-template <bool INV, int K, int NP, bool MUL, bool APX>
+template <bool INV, int K, int NP, bool MUL, bool APX, bool IND>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const fast_pass p) {
+	static_assert(!(IND && MUL), "no indirect fused product");
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -480,12 +486,13 @@ ntt_rows_kernel(const fast_pass p) {
 		const ulonglong2 *twt = sm_tw + ((size_t) h << K);
 		bool active[NP];
 		u64 off[NP];
+		u64 *dbase[NP];   /* IND only */
 		u64 x[NP][8];
 #if ROWS_PREFETCH
 		/* pull the tile this slot takes in the next iteration towards the
 		 * SM while this one is being computed: one 128-byte line per lane
 		 * of the group, no registers held */
-		{
+		if (!IND) {
 			const unsigned nidx = idx + C::groups_per_cta;
 			const unsigned nh = nidx & (hgroup - 1);
 			const unsigned nbl = (nidx >> p.hgroup_log2) * NP;
@@ -502,8 +509,19 @@ ntt_rows_kernel(const fast_pass p) {
 			const unsigned bl = bg * NP + pp;
 			active[pp] = idx < nitems && bl < nb;
 			const u64 poly = (b0 + bl) * p.limbs + limb;
-			off[pp] = (poly << L) + ((u64) (H0 + h) << K);
-			const u64 *sp = p.src + off[pp] + tb_first;
+			const u64 *sp;
+			if (IND) {
+				off[pp] = (u64) (H0 + h) << K;
+				ntt_ptrs ent = { NULL, NULL };
+				if (active[pp]) {
+					ent = p.tab[poly];
+				}
+				dbase[pp] = ent.dst;
+				sp = (p.tab_second ? ent.dst : ent.src) + off[pp] + tb_first;
+			} else {
+				off[pp] = (poly << L) + ((u64) (H0 + h) << K);
+				sp = p.src + off[pp] + tb_first;
+			}
 			if (G::eoff(first, 1) == 1) {
 				/* registers (e, e+1) are adjacent coefficients (the layout of
 				 * the deepest round): 128-bit loads */
@@ -606,7 +624,7 @@ ntt_rows_kernel(const fast_pass p) {
 #pragma unroll
 		for (int pp = 0; pp < NP; pp++) {
 			if (active[pp]) {
-				u64 *dp = p.dst + off[pp] + tb_last;
+				u64 *dp = (IND ? dbase[pp] : p.dst) + off[pp] + tb_last;
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					if (canon) {
@@ -821,7 +839,7 @@ template <int NP> struct col_vec;
 template <> struct col_vec<1> { typedef u64 type; };
 template <> struct col_vec<2> { typedef ulonglong2 type; };
 
-template <bool INV, int K, int CL, int NP, bool APX>
+template <bool INV, int K, int CL, int NP, bool APX, bool IND>
 __global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
 		((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
 			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) > 0
@@ -853,7 +871,14 @@ ntt_cols_kernel(const fast_pass p) {
 	const int t = threadIdx.x >> C::cthreads_log2;         /* row group */
 	constexpr int first = INV ? G::rounds - 1 : 0;
 	constexpr int last = INV ? 0 : G::rounds - 1;
-	const u64 base = (poly << L) + (H << (L - s0)) + (cg << CL) + c;
+	const u64 base = (IND ? 0 : (poly << L)) + (H << (L - s0)) + (cg << CL) + c;
+	const u64 *src_base = p.src;
+	u64 *dst_base = p.dst;
+	if (IND) {
+		const ntt_ptrs ent = p.tab[poly];
+		src_base = p.tab_second ? ent.dst : ent.src;
+		dst_base = ent.dst;
+	}
 
 	__shared__ __align__(8) u64 tw_bar;
 	if (threadIdx.x == 0) {
@@ -870,7 +895,7 @@ ntt_cols_kernel(const fast_pass p) {
 #endif
 	u64 x[NP][8];
 	{
-		const u64 *sp = p.src + base + ((u64) G::tbase(first, t) << low_bits);
+		const u64 *sp = src_base + base + ((u64) G::tbase(first, t) << low_bits);
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
 			const vec_t v = *(const vec_t *) (sp + ((u64) G::eoff(first, e) << low_bits));
@@ -929,7 +954,7 @@ ntt_cols_kernel(const fast_pass p) {
 	}
 
 	pdl_launch_dependents();   /* only this CTA's stores remain */
-	u64 *dp = p.dst + base + ((u64) G::tbase(last, t) << low_bits);
+	u64 *dp = dst_base + base + ((u64) G::tbase(last, t) << low_bits);
 #pragma unroll
 	for (int e = 0; e < 8; e++) {
 		vec_t v;
@@ -973,13 +998,27 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
+	if constexpr (!MUL) {
+		if (p.tab) {
+			if (smem > 48 * 1024) {
+				CUDA_CHECK(cudaFuncSetAttribute(
+							ntt_rows_kernel<INV, K, NP, false, APX, true>,
+							cudaFuncAttributeMaxDynamicSharedMemorySize,
+							(int) smem));
+			}
+			launch_fast(ctx, ntt_rows_kernel<INV, K, NP, false, APX, true>,
+					(unsigned) blocks, FAST_THREADS, smem, p);
+			return;
+		}
+	}
 	if (smem > 48 * 1024) {
 		/* per device, and cheap: set it on every such launch */
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_kernel<INV, K, NP, MUL, APX>,
+		CUDA_CHECK(cudaFuncSetAttribute(
+					ntt_rows_kernel<INV, K, NP, MUL, APX, false>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	launch_fast(ctx, ntt_rows_kernel<INV, K, NP, MUL, APX>, (unsigned) blocks,
-			FAST_THREADS, smem, p);
+	launch_fast(ctx, ntt_rows_kernel<INV, K, NP, MUL, APX, false>,
+			(unsigned) blocks, FAST_THREADS, smem, p);
 }
 
 template <bool INV, int K, bool APX>
@@ -1009,12 +1048,24 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const u64 blocks = (p.polys << p.s0) << (low_bits - CL);
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
+	if (p.tab) {
+		if (smem > 48 * 1024) {
+			CUDA_CHECK(cudaFuncSetAttribute(
+						ntt_cols_kernel<INV, K, CL, NP, APX, true>,
+						cudaFuncAttributeMaxDynamicSharedMemorySize,
+						(int) smem));
+		}
+		launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX, true>,
+				(unsigned) blocks, C::threads, smem, p);
+		return;
+	}
 	if (smem > 48 * 1024) {
-		CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel<INV, K, CL, NP, APX>,
+		CUDA_CHECK(cudaFuncSetAttribute(
+					ntt_cols_kernel<INV, K, CL, NP, APX, false>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
-	launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX>, (unsigned) blocks,
-			C::threads, smem, p);
+	launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX, false>,
+			(unsigned) blocks, C::threads, smem, p);
 }
 
 /* 256 threads per CTA: 2^(12-K) columns with two columns per thread, 2^(11-K)
@@ -1096,9 +1147,12 @@ static fast_plan plan_fast(unsigned log2n) {
 template <bool INV, bool APX>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
-		unsigned log2n, const u64 *src2 = NULL) {
+		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
+	p.tab = tab;
+	p.tab_second = 0;
+	VK_REQUIRE(!tab || !pl.lead, "internal: indirect batch of n > 2^18");
 	p.src2 = NULL;
 	p.descs = descs;
 	p.limbs = (unsigned) limbs;
@@ -1130,6 +1184,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 			p.s0 = pl.lead;
 			run_cols_k<false, APX>(ctx, p, pl.kcol);
 			cur = dst;
+			p.tab_second = 1;
 		}
 		p.src = cur;
 		p.dst = dst;
@@ -1142,6 +1197,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		p.s0 = pl.lead + pl.kcol;
 		run_rows_k<true, APX>(ctx, p, pl.krow);
 		p.src2 = NULL;
+		p.tab_second = 1;
 		if (pl.kcol) {
 			p.src = dst;
 			p.s0 = pl.lead;
@@ -1212,6 +1268,8 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		uint64_t polys, unsigned log2n) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
+	p.tab = NULL;
+	p.tab_second = 0;
 	p.src2 = NULL;
 	p.descs = descs;
 	p.limbs = (unsigned) limbs;
@@ -1339,4 +1397,23 @@ bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		run_fast_polymul<false>(ctx, a, b, tmp, dst, descs, limbs, polys, log2n);
 	}
 	return true;
+}
+
+bool ntt_indirect_supported(unsigned log2n, uint64_t q) {
+	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
+	return !force_generic && q < (1ull << 62) && log2n >= 3 && log2n <= 18;
+}
+
+void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
+		const ntt_ptrs *tab, const limb_desc *desc, uint64_t polys,
+		unsigned log2n, uint64_t q) {
+	VK_REQUIRE(ntt_indirect_supported(log2n, q),
+			"internal: indirect batch outside the fast path");
+	if (use_approx(q, log2n)) {
+		if (inverse) run_fast<true, true>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+		else run_fast<false, true>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+	} else {
+		if (inverse) run_fast<true, false>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+		else run_fast<false, false>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+	}
 }

@@ -10,6 +10,8 @@
  */
 #include <inttypes.h>
 #include <string.h>
+#include <unordered_set>
+#include <vector>
 
 #include "common.cuh"
 #include "vkhel_ext.h"
@@ -21,7 +23,7 @@ static void enter(const struct vkhel_ctx *ctx) {
 /* Device pointer of a vector for an operation on the compute stream.  If an
  * asynchronous upload/download of this vector is still in flight on a copy
  * stream, the compute stream is made to wait for it first (once). */
-static inline u64 *dev_u64(const struct vkhel_vector *v) {
+static inline u64 *dev_u64_nodefer(const struct vkhel_vector *v) {
 	struct vkhel_vector *vec = (struct vkhel_vector *) v;
 	if (v->xfer_pending) {
 		CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(vec->ctx),
@@ -30,6 +32,145 @@ static inline u64 *dev_u64(const struct vkhel_vector *v) {
 	}
 	vec->last_op = ++vec->ctx->dev.op_serial;
 	return (u64 *) v->device.ptr;
+}
+
+/* ---- deferred single-vector transforms ------------------------------------------
+ * The reference API transforms one vector per call (src/vector.c:513-657), and
+ * an application with many small polynomials calls it in a loop; launched one
+ * by one those calls are bound by launch overhead (two kernels, 8 us), not by
+ * the GPU.  vkhel_vector_forward_transform / _inverse_transform therefore only
+ * RECORD the transform.  Consecutive transforms of the same direction and
+ * tables on unrelated vectors accumulate and are launched as ONE indirect
+ * batch (a table of per-polynomial pointers) as soon as anything else needs
+ * the context: another kind of operation, a vector of the batch being touched
+ * again, a transfer, map, sync, a timer, destroy.  Nothing is observable
+ * through the API before one of those, so the results are those of the
+ * immediate launches.  A single recorded transform is launched exactly as
+ * before.  $VKHEL_NO_DEFER=1 turns recording off. */
+#define DEFER_MAX 4096
+
+struct defer_queue {
+	bool inverse;
+	struct vkhel_ntt_tables *ntt;
+	std::vector<ntt_ptrs> items;
+	std::unordered_set<const void *> reads, writes;
+	/* pinned staging for the pointer table: two halves used alternately,
+	 * each guarded by an event recorded after the copy that reads it */
+	ntt_ptrs *stage[2];
+	cudaEvent_t staged[2];
+	int half;
+};
+
+static defer_queue *defer_get(struct vkhel_ctx *ctx) {
+	if (!ctx->dev.defer) {
+		defer_queue *dq = new defer_queue();
+		dq->inverse = false;
+		dq->ntt = NULL;
+		dq->half = 0;
+		for (int i = 0; i < 2; i++) {
+			CUDA_CHECK(cudaHostAlloc((void **) &dq->stage[i],
+						DEFER_MAX * sizeof(ntt_ptrs), cudaHostAllocDefault));
+			CUDA_CHECK(cudaEventCreateWithFlags(&dq->staged[i],
+						cudaEventDisableTiming));
+		}
+		ctx->dev.defer = dq;
+	}
+	return (defer_queue *) ctx->dev.defer;
+}
+
+void defer_flush(struct vkhel_ctx *ctx) {
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	if (!dq || dq->items.empty()) {
+		return;
+	}
+	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+	struct vkhel_ntt_tables *ntt = dq->ntt;
+	const size_t count = dq->items.size();
+	const limb_desc *desc = ntt_tables_device_desc(ctx, ntt);
+	if (count == 1) {
+		launch_ntt(ctx, dq->inverse, dq->items[0].src, dq->items[0].dst, desc,
+				1, 1, (unsigned) ntt->log2n, ntt->q);
+	} else {
+		const int h = dq->half;
+		dq->half ^= 1;
+		/* the copy that last read this half of the staging buffer */
+		CUDA_CHECK(cudaEventSynchronize(dq->staged[h]));
+		memcpy(dq->stage[h], dq->items.data(), count * sizeof(ntt_ptrs));
+		ntt_ptrs *tab = (ntt_ptrs *) device_alloc(ctx, count * sizeof(ntt_ptrs));
+		CUDA_CHECK(cudaMemcpyAsync(tab, dq->stage[h], count * sizeof(ntt_ptrs),
+					cudaMemcpyHostToDevice, ctx_stream(ctx)));
+		CUDA_CHECK(cudaEventRecord(dq->staged[h], ctx_stream(ctx)));
+		launch_ntt_indirect(ctx, dq->inverse, tab, desc, count,
+				(unsigned) ntt->log2n, ntt->q);
+		device_free(ctx, tab);   /* stream-ordered: after the kernels */
+		ctx->dev.deferred_batches++;
+		ctx->dev.deferred_transforms += count;
+	}
+	dq->items.clear();
+	dq->reads.clear();
+	dq->writes.clear();
+	dq->ntt = NULL;
+}
+
+void defer_flush_tables(struct vkhel_ctx *ctx,
+		const struct vkhel_ntt_tables *ntt) {
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	if (dq && dq->ntt == ntt) {
+		defer_flush(ctx);
+	}
+}
+
+void defer_destroy(struct vkhel_ctx *ctx) {
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	if (!dq) {
+		return;
+	}
+	defer_flush(ctx);
+	for (int i = 0; i < 2; i++) {
+		CUDA_CHECK(cudaEventSynchronize(dq->staged[i]));
+		CUDA_CHECK(cudaEventDestroy(dq->staged[i]));
+		CUDA_CHECK(cudaFreeHost(dq->stage[i]));
+	}
+	delete dq;
+	ctx->dev.defer = NULL;
+}
+
+/* Record the transform if it can join (or start) a deferred batch; false when
+ * the caller has to launch it itself. */
+static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
+		struct vkhel_vector *result, struct vkhel_ntt_tables *ntt) {
+	static const bool off = getenv("VKHEL_NO_DEFER") != NULL;
+	struct vkhel_ctx *ctx = result->ctx;
+	if (off || !ntt_indirect_supported((unsigned) ntt->log2n, ntt->q)) {
+		return false;
+	}
+	defer_queue *dq = defer_get(ctx);
+	const void *rd = operand->device.ptr, *wr = result->device.ptr;
+	if (!dq->items.empty()
+			&& (dq->inverse != inverse || dq->ntt != ntt
+				|| dq->items.size() >= DEFER_MAX
+				|| dq->writes.count(rd) || dq->writes.count(wr)
+				|| dq->reads.count(wr))) {
+		/* different batch, or this transform depends on a recorded one (or
+		 * overwrites what a recorded one still has to read) */
+		defer_flush(ctx);
+	}
+	ntt_ptrs ent;
+	ent.src = dev_u64_nodefer(operand);
+	ent.dst = dev_u64_nodefer(result);
+	dq->inverse = inverse;
+	dq->ntt = ntt;
+	dq->items.push_back(ent);
+	dq->reads.insert(rd);
+	dq->writes.insert(wr);
+	return true;
+}
+
+/* Device pointer of a vector for an operation that is launched now: recorded
+ * transforms go first. */
+static inline u64 *dev_u64(const struct vkhel_vector *v) {
+	defer_flush(v->ctx);
+	return dev_u64_nodefer(v);
 }
 
 /* An event on the compute stream that covers every operation up to serial
@@ -62,6 +203,7 @@ static cudaEvent_t fork_event_covering(struct vkhel_ctx *ctx, uint64_t serial,
  * transform of this one) and after the previous transfer of this vector */
 static void xfer_begin(struct vkhel_vector *vec, cudaStream_t copy) {
 	struct vkhel_ctx *ctx = vec->ctx;
+	defer_flush(ctx);
 	cudaEvent_t fork = fork_event_covering(ctx, vec->last_op, vec->exposed);
 	CUDA_CHECK(cudaStreamWaitEvent(copy, fork, 0));
 	if (!vec->xfer_event) {
@@ -435,6 +577,11 @@ extern "C" void vkhel_vector_forward_transform(
 	DBG("forward transform (degree: %" PRIu64 " mod: %" PRIu64
 			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
 	DBG_VEC("operand", operand);
+	check_ntt("forward_transform", operand, result, ntt, ntt->n);
+	if (ntt->n >= 2 && defer_transform(false, operand, result, ntt)) {
+		DBG_VEC("result", result);
+		return;
+	}
 	vkhel_vector_forward_transform_batch(operand, result, ntt, 1);
 	DBG_VEC("result", result);
 }
@@ -445,6 +592,12 @@ extern "C" void vkhel_vector_inverse_transform(
 	DBG("inverse transform (degree: %" PRIu64 " mod: %" PRIu64
 			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
 	DBG_VEC("operand", operand);
+	check_ntt("inverse_transform", operand, result, ntt, ntt->n);
+	if (ntt->n >= 2 && result->length == ntt->n
+			&& defer_transform(true, operand, result, ntt)) {
+		DBG_VEC("result", result);
+		return;
+	}
 	vkhel_vector_inverse_transform_batch(operand, result, ntt, 1);
 	/* The reference scales every element of result, not just the first n
 	 * (vector.c:635-638 run elemmulconst over result->length).
