@@ -43,7 +43,7 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 
 .PHONY: all libs oracle refbins examples tools clean check check-host
 all: libs oracle refbins examples
-examples: $(BIN_DIR)/multi_gpu
+examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop
 libs: $(SHARED) $(STATIC)
 refbins: $(REF_BINS)
 
@@ -77,6 +77,11 @@ $(BIN_DIR)/ref_test_%: $(REF)/test/%.c $(STATIC)
 
 # this repository's own example: limb-sharded transform over every visible GPU
 $(BIN_DIR)/multi_gpu: examples/multi_gpu.c $(STATIC)
+	@mkdir -p $(BIN_DIR)
+	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# the reference API in a loop over separate vectors (recorded transforms)
+$(BIN_DIR)/api_loop: examples/api_loop.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 
