@@ -37,6 +37,8 @@ struct vkhel_ntt_tables {
 };
 
 void vkhel_ntt_tables_dbgprint(struct vkhel_ntt_tables *);
+/* struct + arrays + scalars, arrays not yet filled (ntt_tables.c) */
+struct vkhel_ntt_tables *ntt_tables_alloc(uint64_t n, uint64_t q, uint64_t w);
 
 #ifdef __cplusplus
 }

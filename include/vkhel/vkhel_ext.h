@@ -31,6 +31,14 @@ void vkhel_ctx_sync(struct vkhel_ctx *);
 /* the context's cudaStream_t, for callers that interleave their own work */
 void *vkhel_ctx_stream(struct vkhel_ctx *);
 
+/* vkhel_ntt_tables_create (reference src/ntt_tables.c:65-80) with the four
+ * arrays computed on the context's GPU, one thread per power of w, and the
+ * device mirror of the tables left in place for the transforms; same values,
+ * same struct, destroyed with vkhel_ntt_tables_destroy.  The plain
+ * vkhel_ntt_tables_create stays a host function (it takes no context). */
+struct vkhel_ntt_tables *vkhel_ntt_tables_create_on(struct vkhel_ctx *,
+		uint64_t n, uint64_t q, uint64_t w);
+
 /* ---- pinned host memory + asynchronous transfers --------------------------
  * (reference: map/unmap staging, src/vector.c:262-296) */
 void *vkhel_host_alloc(size_t bytes);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "vkhel_ctx_launch_count": (_u64, [_vp]),
     "vkhel_ctx_flush_l2": (None, [_vp]),
     "vkhel_ctx_flush": (None, [_vp]),
+    "vkhel_ntt_tables_create_on": (_vp, [_vp, _u64, _u64, _u64]),
     "vkhel_ctx_deferred_stats": (None, [_vp, _p64, _p64]),
 }
 
@@ -134,9 +135,13 @@ def host_alloc(count):
 class NttTables:
     """struct vkhel_ntt_tables (vkhel_ntt_tables_create / _destroy)"""
 
-    def __init__(self, n, q, w):
+    def __init__(self, n, q, w, ctx=None):
+        """ctx given: vkhel_ntt_tables_create_on (generated on that GPU)"""
         self.n, self.q, self.w = n, q, w
-        self.handle = lib().vkhel_ntt_tables_create(n, q, w)
+        if ctx is None:
+            self.handle = lib().vkhel_ntt_tables_create(n, q, w)
+        else:
+            self.handle = lib().vkhel_ntt_tables_create_on(ctx.handle, n, q, w)
 
     def _field(self, index):
         # struct layout of include/priv/ntt_tables.h: n, q, w, then 4 pointers

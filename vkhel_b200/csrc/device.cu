@@ -370,6 +370,28 @@ static void fill_desc(const struct vkhel_ntt_tables *ntt, limb_desc *desc,
 	desc->mm_s = m.s;
 }
 
+/* Mirrors outlive contexts (tables belong to none), so they cannot come from a
+ * context's pool; plain cudaMalloc of a few MiB takes tens of milliseconds on
+ * this platform (measured: 18-85 ms each, tools/tables_bench.py).  They are
+ * taken from the device's default stream-ordered pool instead, which is kept
+ * from trimming; ntt_tables_release_device returns them with cudaFree. */
+void *ntt_tables_mirror_alloc(struct vkhel_ctx *ctx, size_t bytes) {
+	ctx_enter(ctx);
+	static bool configured[VKHEL_MAX_DEVICES];
+	const int device = ctx->dev.device;
+	if (!configured[device]) {
+		cudaMemPool_t pool;
+		CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+		uint64_t threshold = UINT64_MAX;
+		CUDA_CHECK(cudaMemPoolSetAttribute(pool,
+					cudaMemPoolAttrReleaseThreshold, &threshold));
+		configured[device] = true;
+	}
+	void *ptr = NULL;
+	CUDA_CHECK(cudaMallocAsync(&ptr, bytes, ctx_stream(ctx)));
+	return ptr;
+}
+
 static void *ensure_mirror(struct vkhel_ctx *ctx,
 		struct vkhel_ntt_tables *ntt) {
 	const int device = ctx->dev.device;
@@ -382,8 +404,7 @@ static void *ensure_mirror(struct vkhel_ctx *ctx,
 			"nt_inverse_mod works in int64_t)");
 	const size_t pair_bytes = 2 * ntt->n * sizeof(ulonglong2);
 	const size_t bytes = sizeof(limb_desc) + pair_bytes;
-	char *dev_buf = NULL;
-	CUDA_CHECK(cudaMalloc(&dev_buf, bytes));
+	char *dev_buf = (char *) ntt_tables_mirror_alloc(ctx, bytes);
 	char *host_buf = (char *) malloc(bytes);
 	VK_REQUIRE(host_buf, "out of host memory");
 	fill_desc(ntt, (limb_desc *) host_buf,
@@ -395,12 +416,28 @@ static void *ensure_mirror(struct vkhel_ctx *ctx,
 		pairs[ntt->n + k] = make_ulonglong2(ntt->inv_roots_of_unity[k],
 				ntt->inv_roots_barrett_factors[k]);
 	}
-	/* synchronous copy: complete before any kernel that reads it is
-	 * enqueued, and the host buffer can be freed right away */
-	CUDA_CHECK(cudaMemcpy(dev_buf, host_buf, bytes, cudaMemcpyHostToDevice));
+	/* on the context's stream, after the allocation; completed here so that
+	 * the host buffer can be freed right away and other contexts of this
+	 * device can use the mirror */
+	CUDA_CHECK(cudaMemcpyAsync(dev_buf, host_buf, bytes, cudaMemcpyHostToDevice,
+				ctx_stream(ctx)));
+	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
 	free(host_buf);
 	ntt->dev_pairs[device] = dev_buf;
 	return dev_buf;
+}
+
+/* tables_device.cu generated the pairs in place: write the descriptor in front
+ * of them and register the buffer as this device's mirror */
+void ntt_tables_adopt_mirror(struct vkhel_ctx *ctx,
+		struct vkhel_ntt_tables *ntt, char *dev_buf) {
+	ctx_enter(ctx);
+	limb_desc desc;
+	fill_desc(ntt, &desc, (const ulonglong2 *) (dev_buf + sizeof(limb_desc)));
+	CUDA_CHECK(cudaMemcpyAsync(dev_buf, &desc, sizeof(desc),
+				cudaMemcpyHostToDevice, ctx_stream(ctx)));
+	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
+	ntt->dev_pairs[ctx->dev.device] = dev_buf;
 }
 
 const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,
@@ -420,7 +457,10 @@ extern "C" void ntt_tables_release_device(struct vkhel_ntt_tables *ntt) {
 			continue;
 		}
 		enter_device(device);
-		/* cudaFree waits for work that may still read the mirror */
+		/* kernels of any context on this device may still read the mirror,
+		 * and cudaFree does not wait for them when the block comes from a
+		 * stream-ordered pool */
+		CUDA_CHECK(cudaDeviceSynchronize());
 		CUDA_CHECK(cudaFree(ntt->dev_pairs[device]));
 		ntt->dev_pairs[device] = NULL;
 	}

@@ -58,8 +58,10 @@ static void fill_power_chain(uint64_t *out, uint64_t n, unsigned log2n,
 	}
 }
 
-struct vkhel_ntt_tables *vkhel_ntt_tables_create(uint64_t n,
-		uint64_t q, uint64_t w) {
+/* allocate the struct and its four arrays and fill in the scalars; the arrays
+ * are filled by the caller (host chain below, or the device generator of
+ * tables_device.cu) */
+struct vkhel_ntt_tables *ntt_tables_alloc(uint64_t n, uint64_t q, uint64_t w) {
 	assert(n >= 1 && (n & (n - 1)) == 0 && "n must be a power of two");
 	assert(q >= 2);
 
@@ -79,6 +81,16 @@ struct vkhel_ntt_tables *vkhel_ntt_tables_create(uint64_t n,
 			&& ntt->roots_barrett_factors
 			&& ntt->inv_roots_barrett_factors);
 
+	/* n^-1 for the inverse transform's scaling (reference vector.c:633) */
+	ntt->inv_n = nt_inverse_mod(n % q, q);
+	ntt->inv_n_shoup = nt_compute_barrett_factor(ntt->inv_n, q, 64);
+	return ntt;
+}
+
+struct vkhel_ntt_tables *vkhel_ntt_tables_create(uint64_t n,
+		uint64_t q, uint64_t w) {
+	struct vkhel_ntt_tables *ntt = ntt_tables_alloc(n, q, w);
+
 	const uint64_t w_red = w % q;
 	fill_power_chain(ntt->roots_of_unity, n, ntt->log2n, w_red, q);
 	/* w = 0 has no inverse; the reference would fault in that case too */
@@ -91,10 +103,6 @@ struct vkhel_ntt_tables *vkhel_ntt_tables_create(uint64_t n,
 		ntt->inv_roots_barrett_factors[i] = nt_compute_barrett_factor(
 				ntt->inv_roots_of_unity[i], q, 64);
 	}
-
-	/* n^-1 for the inverse transform's scaling (reference vector.c:633) */
-	ntt->inv_n = nt_inverse_mod(n % q, q);
-	ntt->inv_n_shoup = nt_compute_barrett_factor(ntt->inv_n, q, 64);
 	return ntt;
 }
 
