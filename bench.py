@@ -342,6 +342,36 @@ def run_native_arm(args):
     ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
     ok = ok and bool(np.array_equal(host_out.array, host_in.array))
 
+    # the same trip through the reference's 18 calls only (one vector per
+    # polynomial, pageable host memory): copy_from_host, forward_transform,
+    # inverse_transform, map (read the result), unmap.  A bounded sample of
+    # the batch: LEGACY_POLYS polynomials over the first limbs.
+    legacy_polys = 64
+    legacy_vecs = [ctx.vector(N, zero=False) for _ in range(legacy_polys)]
+    legacy_in = np.array(host_in.array[:legacy_polys * N])   # pageable copy
+    legacy_out = np.empty_like(legacy_in)
+
+    def step_legacy():
+        for p, v in enumerate(legacy_vecs):
+            v.copy_from_host(legacy_in[p * N:(p + 1) * N])
+        for p, v in enumerate(legacy_vecs):
+            ctx.forward_transform(v, v, tables[p % LIMBS])
+        for p, v in enumerate(legacy_vecs):
+            ctx.inverse_transform(v, v, tables[p % LIMBS])
+        for p, v in enumerate(legacy_vecs):
+            legacy_out[p * N:(p + 1) * N] = v.to_host()
+
+    step_legacy()
+    ctx.sync()
+    t_legacy = time.perf_counter()
+    legacy_steps = 3
+    for _ in range(legacy_steps):
+        step_legacy()
+    ctx.sync()
+    t_legacy = (time.perf_counter() - t_legacy) / legacy_steps
+    ok = ok and bool(np.array_equal(legacy_out, legacy_in))
+    legacy_value = world * 2 * legacy_polys / t_legacy
+
     ntts_per_step = 2 * POLYS
     ms_per_step = ms_total / args.steps
     value = world * ntts_per_step / (ms_per_step * 1e-3)
@@ -373,6 +403,16 @@ def run_native_arm(args):
                             "inverse_transform_rns -> vkhel_vector_download;"
                             " copies on the context's H2D/D2H streams "
                             "overlap with each other and with compute"},
+            "e2e_reference_api": {
+                "value": legacy_value, "unit": "NTT/s",
+                "sample": "%d polynomials, one vkhel_vector each" % legacy_polys,
+                "path": "the reference's 18 entry points only, pageable host "
+                        "memory: vkhel_vector_copy_from_host -> "
+                        "vkhel_vector_forward_transform -> "
+                        "vkhel_vector_inverse_transform -> vkhel_vector_map "
+                        "+ copy out + vkhel_vector_unmap (which writes the "
+                        "vector back, as the reference does); host wall "
+                        "clock"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
@@ -414,7 +454,7 @@ def run_native_arm(args):
         print(json.dumps(line))
 
     timer.destroy()
-    for v in [data, work] + slices[0] + slices[1]:
+    for v in [data, work] + slices[0] + slices[1] + legacy_vecs:
         v.destroy()
     for t in tables:
         t.destroy()

@@ -109,6 +109,45 @@ def test_shared_operand_and_mixed_tables(ctx):
     t1.destroy(), t2.destroy()
 
 
+@pytest.mark.parametrize("log2n,limbs,batch,extra", [(10, 5, 7, 0),
+                                                     (13, 3, 4, 2),
+                                                     (16, 4, 2, 0)])
+def test_rns_polynomials_as_one_vector_per_limb(ctx, log2n, limbs, batch,
+                                                 extra):
+    """the HE pattern of the reference API: every limb of every polynomial is
+    its own vector with its own tables.  Equal counts per table: one launch
+    laid out [batch][limbs]; unequal: one launch per table."""
+    n = 1 << log2n
+    primes = params.ntt_primes(limbs)
+    ts = [Tables(n, q) for q in primes]
+    rng = np.random.default_rng(limbs * batch)
+    xs = [[rand_mod(rng, n, primes[l]) for l in range(limbs)]
+          for _ in range(batch + extra)]
+    vs = [[ctx.from_host(x) for x in row] for row in xs[:batch]]
+    vs += [[ctx.from_host(xs[batch + e][0])] for e in range(extra)]
+    ctx.sync()
+    b0, t0 = ctx.deferred_stats
+    for row in vs:
+        for l, v in enumerate(row):
+            ctx.forward_transform(v, v, ts[l].lib)
+    ctx.flush()
+    b1, t1 = ctx.deferred_stats
+    assert t1 - t0 == batch * limbs + extra
+    assert b1 - b0 == (1 if extra == 0 else limbs)
+    for row, xrow in zip(vs, xs):
+        for l, (v, x) in enumerate(zip(row, xrow)):
+            assert np.array_equal(v.to_host(), oracle.forward(x, ts[l].ora))
+    for row in vs:
+        for l, v in enumerate(row):
+            ctx.inverse_transform(v, v, ts[l].lib)
+    for row, xrow in zip(vs, xs):
+        for v, x in zip(row, xrow):
+            assert np.array_equal(v.to_host(), x)
+            v.destroy()
+    for t in ts:
+        t.destroy()
+
+
 def test_recorded_transforms_meet_other_operations(ctx):
     """element-wise ops, transfers, dup, destroy of vectors and of the tables
     while transforms are still only recorded"""

@@ -387,6 +387,228 @@ struct gs_v19 { static const char *name() { return "GS v19 whole Shoup product a
 		y = shoup3_ptx(d, c.w, c.wp, nq);
 	} };
 
+
+/* ---- V20: x' comes out of the multiply chain (accumulator starts at xr), y' = (2xr+3q) - x' ---- */
+__device__ __forceinline__ u64 shoup3_acc_ptx(u64 acc, u64 y, u64 w, u64 wp, u64 nq) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) w, w1 = (u32) (w >> 32);
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32), n0 = (u32) nq, n1 = (u32) (nq >> 32);
+	const u32 a0 = (u32) acc, a1 = (u32) (acc >> 32);
+	u32 t0, t1;
+	asm("{\n\t"
+		".reg .u32 r0, h0, h1;\n\t"
+		"mul.lo.u32 r0, %2, %7;\n\t"
+		"mul.hi.u32 h0, %2, %7;\n\t"
+		"mad.lo.cc.u32 r0, %3, %6, r0;\n\t"
+		"madc.hi.cc.u32 h0, %3, %6, h0;\n\t"
+		"addc.u32 h1, 0, 0;\n\t"
+		"mad.lo.cc.u32 h0, %3, %7, h0;\n\t"
+		"madc.hi.u32 h1, %3, %7, h1;\n\t"
+		/* t = acc + lo64(y*w) + lo64(h*nq) */
+		"mad.lo.cc.u32 %0, %2, %4, %10;\n\t"
+		"madc.hi.u32 %1, %2, %4, %11;\n\t"
+		"mad.lo.cc.u32 %0, h0, %8, %0;\n\t"
+		"madc.hi.u32 %1, h0, %8, %1;\n\t"
+		"mad.lo.u32 %1, %2, %5, %1;\n\t"
+		"mad.lo.u32 %1, %3, %4, %1;\n\t"
+		"mad.lo.u32 %1, h0, %9, %1;\n\t"
+		"mad.lo.u32 %1, h1, %8, %1;\n\t"
+		"}" : "=&r"(t0), "=&r"(t1)
+		: "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1),
+		  "r"(a0), "r"(a1));
+	return ((u64) t1 << 32) | t0;
+}
+struct ct_v20 { static const char *name() { return "CT v20 = v19, x' out of the chain (acc = xr), y' = 2xr+3q-x'"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, threeq);
+		const u64 xn = shoup3_acc_ptx(xr, y, c.w, c.wp, nq);
+		y = xr + xr + threeq - xn; x = xn;
+	} };
+struct ct_v24 { static const char *name() { return "CT v24 = v19 without csub (bound +3q per stage)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = x;
+		const u64 t = shoup3_ptx(y, c.w, c.wp, nq);
+		x = xr + t; y = xr - t + threeq;
+	} };
+struct ct_v25 { static const char *name() { return "CT v25 = v20 without csub"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = x;
+		const u64 xn = shoup3_acc_ptx(xr, y, c.w, c.wp, nq);
+		y = xr + xr + threeq - xn; x = xn;
+	} };
+struct gs_v24 { static const char *name() { return "GS v24 = v19 without csub"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 s = x + y, d = x - y + threeq;
+		x = s;
+		y = shoup3_ptx(d, c.w, c.wp, nq);
+	} };
+/* pipe-cost probes: N independent multiply forms per pair */
+struct only_wide_rz { static const char *name() { return "probe: 4x mul.wide.u32 (C = RZ)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u32 a = (u32) x, b = (u32) (x >> 32), d = (u32) y, e = (u32) (y >> 32);
+		u64 r0, r1, r2, r3;
+		asm("mul.wide.u32 %0, %1, %2;" : "=l"(r0) : "r"(a), "r"((u32) c.w));
+		asm("mul.wide.u32 %0, %1, %2;" : "=l"(r1) : "r"(b), "r"((u32) c.wp));
+		asm("mul.wide.u32 %0, %1, %2;" : "=l"(r2) : "r"(d), "r"((u32) c.q));
+		asm("mul.wide.u32 %0, %1, %2;" : "=l"(r3) : "r"(e), "r"((u32) (c.w >> 32)));
+		x = r0 ^ r1; y = r2 ^ r3;
+	} };
+struct only_wide_acc { static const char *name() { return "probe: 4x mad.wide.u32 (64-bit C)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u32 a = (u32) x, b = (u32) (x >> 32), d = (u32) y, e = (u32) (y >> 32);
+		u64 r0, r1;
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r0) : "r"(a), "r"((u32) c.w), "l"(y));
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r0) : "r"(b), "r"((u32) c.wp), "l"(r0));
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r1) : "r"(d), "r"((u32) c.q), "l"(x));
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r1) : "r"(e), "r"((u32) (c.w >> 32)), "l"(r1));
+		x = r0; y = r1;
+	} };
+struct only_hi_acc { static const char *name() { return "probe: 4x mad.hi.u32"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		u32 a = (u32) x, b = (u32) (x >> 32), d = (u32) y, e = (u32) (y >> 32);
+		asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a) : "r"((u32) c.w), "r"(b));
+		asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(b) : "r"((u32) c.wp), "r"(d));
+		asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(d) : "r"((u32) c.q), "r"(e));
+		asm("mad.hi.u32 %0, %0, %1, %2;" : "+r"(e) : "r"((u32) (c.w >> 32)), "r"(a));
+		x = ((u64) b << 32) | a; y = ((u64) e << 32) | d;
+	} };
+struct only_lo { static const char *name() { return "probe: 4x mad.lo.u32"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		u32 a = (u32) x, b = (u32) (x >> 32), d = (u32) y, e = (u32) (y >> 32);
+		asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a) : "r"((u32) c.w), "r"(b));
+		asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b) : "r"((u32) c.wp), "r"(d));
+		asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(d) : "r"((u32) c.q), "r"(e));
+		asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(e) : "r"((u32) (c.w >> 32)), "r"(a));
+		x = ((u64) b << 32) | a; y = ((u64) e << 32) | d;
+	} };
+
+
+/* ---- V26: no IMAD.HI -- three wide products, word sums on the ALU ---- */
+__device__ __forceinline__ u64 shoup3_nohi_ptx(u64 y, u64 w, u64 wp, u64 nq) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) w, w1 = (u32) (w >> 32);
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32), n0 = (u32) nq, n1 = (u32) (nq >> 32);
+	u32 t0, t1;
+	asm("{\n\t"
+		".reg .u32 a0, a1, b0, b1, c0, c1, j, h0, h1;\n\t"
+		".reg .u64 A, B, C;\n\t"
+		"mul.wide.u32 A, %2, %7;\n\t"          /* y0*p1 */
+		"mul.wide.u32 B, %3, %6;\n\t"          /* y1*p0 */
+		"mul.wide.u32 C, %3, %7;\n\t"          /* y1*p1 */
+		"mov.b64 {a0, a1}, A;\n\t"
+		"mov.b64 {b0, b1}, B;\n\t"
+		"mov.b64 {c0, c1}, C;\n\t"
+		"add.cc.u32 j, a0, b0;\n\t"            /* word 1: only its carry */
+		"addc.cc.u32 h0, a1, b1;\n\t"          /* word 2 */
+		"addc.u32 h1, c1, 0;\n\t"              /* word 3 */
+		"add.cc.u32 h0, h0, c0;\n\t"
+		"addc.u32 h1, h1, 0;\n\t"
+		"mul.lo.u32 %0, %2, %4;\n\t"
+		"mul.hi.u32 %1, %2, %4;\n\t"
+		"mad.lo.cc.u32 %0, h0, %8, %0;\n\t"
+		"madc.hi.u32 %1, h0, %8, %1;\n\t"
+		"mad.lo.u32 %1, %2, %5, %1;\n\t"
+		"mad.lo.u32 %1, %3, %4, %1;\n\t"
+		"mad.lo.u32 %1, h0, %9, %1;\n\t"
+		"mad.lo.u32 %1, h1, %8, %1;\n\t"
+		"}" : "=&r"(t0), "=&r"(t1)
+		: "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1));
+	return ((u64) t1 << 32) | t0;
+}
+struct ct_v26 { static const char *name() { return "CT v26 = v19 with three wide products, no IMAD.HI"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, threeq);
+		const u64 t = shoup3_nohi_ptx(y, c.w, c.wp, nq);
+		x = xr + t; y = xr - t + threeq;
+	} };
+/* ---- V27: v26 dropping the word-1 sum as well: h in [H-2, H], product in [0,4q) ---- */
+__device__ __forceinline__ u64 shoup4_ptx(u64 y, u64 w, u64 wp, u64 nq) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) w, w1 = (u32) (w >> 32);
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32), n0 = (u32) nq, n1 = (u32) (nq >> 32);
+	u32 t0, t1;
+	asm("{\n\t"
+		".reg .u32 a0, a1, b0, b1, c0, c1, h0, h1;\n\t"
+		".reg .u64 A, B, C;\n\t"
+		"mul.wide.u32 A, %2, %7;\n\t"
+		"mul.wide.u32 B, %3, %6;\n\t"
+		"mul.wide.u32 C, %3, %7;\n\t"
+		"mov.b64 {a0, a1}, A;\n\t"
+		"mov.b64 {b0, b1}, B;\n\t"
+		"mov.b64 {c0, c1}, C;\n\t"
+		"add.cc.u32 h0, a1, b1;\n\t"
+		"addc.u32 h1, c1, 0;\n\t"
+		"add.cc.u32 h0, h0, c0;\n\t"
+		"addc.u32 h1, h1, 0;\n\t"
+		"mul.lo.u32 %0, %2, %4;\n\t"
+		"mul.hi.u32 %1, %2, %4;\n\t"
+		"mad.lo.cc.u32 %0, h0, %8, %0;\n\t"
+		"madc.hi.u32 %1, h0, %8, %1;\n\t"
+		"mad.lo.u32 %1, %2, %5, %1;\n\t"
+		"mad.lo.u32 %1, %3, %4, %1;\n\t"
+		"mad.lo.u32 %1, h0, %9, %1;\n\t"
+		"mad.lo.u32 %1, h1, %8, %1;\n\t"
+		"}" : "=&r"(t0), "=&r"(t1)
+		: "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1));
+	return ((u64) t1 << 32) | t0;
+}
+struct ct_v27 { static const char *name() { return "CT v27 = v26 without the word-1 sum: [0,4q) product, csub(x,4q)"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 fourq = 2 * c.twoq, nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, fourq);
+		const u64 t = shoup4_ptx(y, c.w, c.wp, nq);
+		x = xr + t; y = xr - t + fourq;
+	} };
+/* ---- V28: v19 with the four narrow products summed apart and the high words of
+ * x' and y' formed by three-input adds (keeps them off the FMA pipe) ---- */
+__device__ __forceinline__ void ct_split_ptx(u64 &x, u64 &y, u64 xr, u64 w, u64 wp, u64 nq, u64 threeq) {
+	const u32 y0 = (u32) y, y1 = (u32) (y >> 32), w0 = (u32) w, w1 = (u32) (w >> 32);
+	const u32 p0 = (u32) wp, p1 = (u32) (wp >> 32), n0 = (u32) nq, n1 = (u32) (nq >> 32);
+	const u32 x0 = (u32) xr, x1 = (u32) (xr >> 32);
+	const u32 m0 = (u32) threeq, m1 = (u32) (threeq >> 32);
+	u32 o0, o1, z0, z1;
+	asm("{\n\t"
+		".reg .u32 r0, h0, h1, t0, t1, s, e0, e1;\n\t"
+		"mul.lo.u32 r0, %4, %9;\n\t"
+		"mul.hi.u32 h0, %4, %9;\n\t"
+		"mad.lo.cc.u32 r0, %5, %8, r0;\n\t"
+		"madc.hi.cc.u32 h0, %5, %8, h0;\n\t"
+		"addc.u32 h1, 0, 0;\n\t"
+		"mad.lo.cc.u32 h0, %5, %9, h0;\n\t"
+		"madc.hi.u32 h1, %5, %9, h1;\n\t"
+		"mul.lo.u32 t0, %4, %6;\n\t"
+		"mul.hi.u32 t1, %4, %6;\n\t"
+		"mad.lo.cc.u32 t0, h0, %10, t0;\n\t"
+		"madc.hi.u32 t1, h0, %10, t1;\n\t"
+		"mul.lo.u32 s, %4, %7;\n\t"            /* narrow products apart */
+		"mad.lo.u32 s, %5, %6, s;\n\t"
+		"mad.lo.u32 s, h0, %11, s;\n\t"
+		"mad.lo.u32 s, h1, %10, s;\n\t"
+		/* x' = xr + t + (s << 32) */
+		"add.cc.u32 %0, %12, t0;\n\t"
+		"addc.u32 %1, %13, t1;\n\t"
+		"add.u32 %1, %1, s;\n\t"
+		/* y' = xr + 3q - t - (s << 32) */
+		"add.cc.u32 e0, %12, %14;\n\t"
+		"addc.u32 e1, %13, %15;\n\t"
+		"sub.cc.u32 %2, e0, t0;\n\t"
+		"subc.u32 %3, e1, t1;\n\t"
+		"sub.u32 %3, %3, s;\n\t"
+		"}" : "=&r"(o0), "=&r"(o1), "=&r"(z0), "=&r"(z1)
+		: "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1),
+		  "r"(x0), "r"(x1), "r"(m0), "r"(m1));
+	x = ((u64) o1 << 32) | o0;
+	y = ((u64) z1 << 32) | z0;
+}
+struct ct_v28 { static const char *name() { return "CT v28 = v19, narrow products apart, 3-input high-word adds"; }
+	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
+		const u64 threeq = c.twoq + c.q, nq = 0 - c.q;
+		const u64 xr = csub_borrow(x, threeq);
+		ct_split_ptx(x, y, xr, c.w, c.wp, nq, threeq);
+	} };
+
 /* ---- GS variants ---- */
 struct gs_v0 { static const char *name() { return "GS v0 harvey (as shipped)"; }
 	__device__ __forceinline__ void operator()(u64 &x, u64 &y, const consts &c) const {
@@ -470,5 +692,7 @@ int main() {
 	run<ct_v4>(sms, c); run<ct_v5>(sms, c); run<ct_v6>(sms, c); run<ct_v7>(sms, c);
 	run<gs_v0>(sms, c); run<gs_v1>(sms, c); run<gs_v2>(sms, c); run<gs_v6>(sms, c);
 	run<only_shoup>(sms, c); run<only_shoup_approx>(sms, c); run<only_mulhi32>(sms, c);
+	run<ct_v26>(sms, c); run<ct_v27>(sms, c); run<ct_v28>(sms, c); run<ct_v20>(sms, c); run<ct_v24>(sms, c); run<ct_v25>(sms, c); run<gs_v24>(sms, c);
+	run<only_wide_rz>(sms, c); run<only_wide_acc>(sms, c); run<only_hi_acc>(sms, c); run<only_lo>(sms, c);
 	return 0;
 }

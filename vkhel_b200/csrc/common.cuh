@@ -109,13 +109,13 @@ bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		u64 *tmp, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max);
 
-/* the same transform on `polys` separate polynomials of one table, polynomial
- * i read from tab[i].src and written to tab[i].dst (tab in device memory);
- * only where ntt_indirect_supported() */
+/* the same transform on `polys` separate polynomials, polynomial i read from
+ * tab[i].src, written to tab[i].dst (tab in device memory) and using
+ * descs[i % limbs]; only where ntt_indirect_supported() */
 bool ntt_indirect_supported(unsigned log2n, uint64_t q);
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
-		const ntt_ptrs *tab, const limb_desc *desc, uint64_t polys,
-		unsigned log2n, uint64_t q);
+		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max);
 
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */

@@ -1405,15 +1405,15 @@ bool ntt_indirect_supported(unsigned log2n, uint64_t q) {
 }
 
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
-		const ntt_ptrs *tab, const limb_desc *desc, uint64_t polys,
-		unsigned log2n, uint64_t q) {
-	VK_REQUIRE(ntt_indirect_supported(log2n, q),
+		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max) {
+	VK_REQUIRE(ntt_indirect_supported(log2n, q_max),
 			"internal: indirect batch outside the fast path");
-	if (use_approx(q, log2n)) {
-		if (inverse) run_fast<true, true>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
-		else run_fast<false, true>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+	if (use_approx(q_max, log2n)) {
+		if (inverse) run_fast<true, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
+		else run_fast<false, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
 	} else {
-		if (inverse) run_fast<true, false>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
-		else run_fast<false, false>(ctx, NULL, NULL, desc, 1, polys, log2n, NULL, tab);
+		if (inverse) run_fast<true, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
+		else run_fast<false, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
 	}
 }

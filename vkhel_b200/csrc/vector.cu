@@ -40,19 +40,28 @@ static inline u64 *dev_u64_nodefer(const struct vkhel_vector *v) {
  * by one those calls are bound by launch overhead (two kernels, 8 us), not by
  * the GPU.  vkhel_vector_forward_transform / _inverse_transform therefore only
  * RECORD the transform.  Consecutive transforms of the same direction and
- * tables on unrelated vectors accumulate and are launched as ONE indirect
- * batch (a table of per-polynomial pointers) as soon as anything else needs
+ * size on unrelated vectors accumulate -- with any mix of tables, e.g. the
+ * limbs of RNS polynomials held as one vector per limb -- and are launched as
+ * ONE indirect batch (a table of per-polynomial pointers; one batch per table
+ * when the tables are not used equally often) as soon as anything else needs
  * the context: another kind of operation, a vector of the batch being touched
  * again, a transfer, map, sync, a timer, destroy.  Nothing is observable
  * through the API before one of those, so the results are those of the
  * immediate launches.  A single recorded transform is launched exactly as
  * before.  $VKHEL_NO_DEFER=1 turns recording off. */
 #define DEFER_MAX 4096
+#define DEFER_TABLES 64
+
+struct defer_item {
+	ntt_ptrs ptrs;
+	unsigned table;     /* index into defer_queue::tables */
+};
 
 struct defer_queue {
 	bool inverse;
-	struct vkhel_ntt_tables *ntt;
-	std::vector<ntt_ptrs> items;
+	uint64_t log2n;
+	std::vector<struct vkhel_ntt_tables *> tables;   /* distinct, <= DEFER_TABLES */
+	std::vector<defer_item> items;
 	std::unordered_set<const void *> reads, writes;
 	/* pinned staging for the pointer table: two halves used alternately,
 	 * each guarded by an event recorded after the copy that reads it */
@@ -65,7 +74,7 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 	if (!ctx->dev.defer) {
 		defer_queue *dq = new defer_queue();
 		dq->inverse = false;
-		dq->ntt = NULL;
+		dq->log2n = 0;
 		dq->half = 0;
 		for (int i = 0; i < 2; i++) {
 			CUDA_CHECK(cudaHostAlloc((void **) &dq->stage[i],
@@ -78,45 +87,113 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 	return (defer_queue *) ctx->dev.defer;
 }
 
+/* one indirect launch: `count` pointer pairs already laid out in `host` as
+ * [batch][limbs] (polynomial i uses descs[i % limbs]) */
+static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
+		const std::vector<ntt_ptrs> &host, const limb_desc *descs,
+		uint64_t limbs, uint64_t q_max) {
+	const size_t count = host.size();
+	size_t done = 0;
+	while (done < count) {
+		/* whole batch entries per piece of at most DEFER_MAX pointers */
+		size_t piece = count - done;
+		if (piece > DEFER_MAX) {
+			piece = DEFER_MAX / limbs * limbs;
+		}
+		const int h = dq->half;
+		dq->half ^= 1;
+		/* the copy that last read this half of the staging buffer */
+		CUDA_CHECK(cudaEventSynchronize(dq->staged[h]));
+		memcpy(dq->stage[h], host.data() + done, piece * sizeof(ntt_ptrs));
+		ntt_ptrs *tab = (ntt_ptrs *) device_alloc(ctx, piece * sizeof(ntt_ptrs));
+		CUDA_CHECK(cudaMemcpyAsync(tab, dq->stage[h], piece * sizeof(ntt_ptrs),
+					cudaMemcpyHostToDevice, ctx_stream(ctx)));
+		CUDA_CHECK(cudaEventRecord(dq->staged[h], ctx_stream(ctx)));
+		launch_ntt_indirect(ctx, dq->inverse, tab, descs, limbs, piece,
+				(unsigned) dq->log2n, q_max);
+		device_free(ctx, tab);   /* stream-ordered: after the kernels */
+		ctx->dev.deferred_batches++;
+		ctx->dev.deferred_transforms += piece;
+		done += piece;
+	}
+}
+
 void defer_flush(struct vkhel_ctx *ctx) {
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
 	if (!dq || dq->items.empty()) {
 		return;
 	}
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
-	struct vkhel_ntt_tables *ntt = dq->ntt;
 	const size_t count = dq->items.size();
-	const limb_desc *desc = ntt_tables_device_desc(ctx, ntt);
+	const size_t ntab = dq->tables.size();
 	if (count == 1) {
-		launch_ntt(ctx, dq->inverse, dq->items[0].src, dq->items[0].dst, desc,
-				1, 1, (unsigned) ntt->log2n, ntt->q);
-	} else {
-		const int h = dq->half;
-		dq->half ^= 1;
-		/* the copy that last read this half of the staging buffer */
-		CUDA_CHECK(cudaEventSynchronize(dq->staged[h]));
-		memcpy(dq->stage[h], dq->items.data(), count * sizeof(ntt_ptrs));
-		ntt_ptrs *tab = (ntt_ptrs *) device_alloc(ctx, count * sizeof(ntt_ptrs));
-		CUDA_CHECK(cudaMemcpyAsync(tab, dq->stage[h], count * sizeof(ntt_ptrs),
-					cudaMemcpyHostToDevice, ctx_stream(ctx)));
-		CUDA_CHECK(cudaEventRecord(dq->staged[h], ctx_stream(ctx)));
-		launch_ntt_indirect(ctx, dq->inverse, tab, desc, count,
+		struct vkhel_ntt_tables *ntt = dq->tables[0];
+		launch_ntt(ctx, dq->inverse, dq->items[0].ptrs.src,
+				dq->items[0].ptrs.dst, ntt_tables_device_desc(ctx, ntt), 1, 1,
 				(unsigned) ntt->log2n, ntt->q);
-		device_free(ctx, tab);   /* stream-ordered: after the kernels */
-		ctx->dev.deferred_batches++;
-		ctx->dev.deferred_transforms += count;
+	} else {
+		/* the recorded transforms are independent of each other, so they
+		 * may be regrouped: by tables (an RNS polynomial held as one vector
+		 * per limb arrives as limb 0, limb 1, ... of polynomial after
+		 * polynomial) */
+		std::vector<std::vector<ntt_ptrs> > by_table(ntab);
+		for (const defer_item &it : dq->items) {
+			by_table[it.table].push_back(it.ptrs);
+		}
+		bool rectangular = true;
+		for (size_t t = 1; t < ntab; t++) {
+			rectangular = rectangular
+				&& by_table[t].size() == by_table[0].size();
+		}
+		if (ntab > 1 && rectangular) {
+			/* one launch for all tables, laid out [batch][limbs] like
+			 * vkhel_vector_forward_transform_rns */
+			uint64_t q_max = 0;
+			for (struct vkhel_ntt_tables *t : dq->tables) {
+				q_max = t->q > q_max ? t->q : q_max;
+			}
+			const size_t batch = by_table[0].size();
+			std::vector<ntt_ptrs> host(count);
+			for (size_t b = 0; b < batch; b++) {
+				for (size_t t = 0; t < ntab; t++) {
+					host[b * ntab + t] = by_table[t][b];
+				}
+			}
+			defer_launch(ctx, dq, host,
+					rns_plan_device_descs(ctx, dq->tables.data(), ntab), ntab,
+					q_max);
+		} else {
+			for (size_t t = 0; t < ntab; t++) {
+				struct vkhel_ntt_tables *ntt = dq->tables[t];
+				if (by_table[t].size() == 1) {
+					launch_ntt(ctx, dq->inverse, by_table[t][0].src,
+							by_table[t][0].dst,
+							ntt_tables_device_desc(ctx, ntt), 1, 1,
+							(unsigned) ntt->log2n, ntt->q);
+				} else {
+					defer_launch(ctx, dq, by_table[t],
+							ntt_tables_device_desc(ctx, ntt), 1, ntt->q);
+				}
+			}
+		}
 	}
 	dq->items.clear();
+	dq->tables.clear();
 	dq->reads.clear();
 	dq->writes.clear();
-	dq->ntt = NULL;
 }
 
 void defer_flush_tables(struct vkhel_ctx *ctx,
 		const struct vkhel_ntt_tables *ntt) {
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
-	if (dq && dq->ntt == ntt) {
-		defer_flush(ctx);
+	if (!dq) {
+		return;
+	}
+	for (const struct vkhel_ntt_tables *t : dq->tables) {
+		if (t == ntt) {
+			defer_flush(ctx);
+			return;
+		}
 	}
 }
 
@@ -146,21 +223,32 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 	}
 	defer_queue *dq = defer_get(ctx);
 	const void *rd = operand->device.ptr, *wr = result->device.ptr;
-	if (!dq->items.empty()
-			&& (dq->inverse != inverse || dq->ntt != ntt
+	unsigned table = 0;
+	if (!dq->items.empty()) {
+		while (table < dq->tables.size() && dq->tables[table] != ntt) {
+			table++;
+		}
+		if (dq->inverse != inverse || dq->log2n != ntt->log2n
 				|| dq->items.size() >= DEFER_MAX
+				|| table >= DEFER_TABLES
 				|| dq->writes.count(rd) || dq->writes.count(wr)
-				|| dq->reads.count(wr))) {
-		/* different batch, or this transform depends on a recorded one (or
-		 * overwrites what a recorded one still has to read) */
-		defer_flush(ctx);
+				|| dq->reads.count(wr)) {
+			/* different batch, or this transform depends on a recorded one
+			 * (or overwrites what a recorded one still has to read) */
+			defer_flush(ctx);
+			table = 0;
+		}
 	}
-	ntt_ptrs ent;
-	ent.src = dev_u64_nodefer(operand);
-	ent.dst = dev_u64_nodefer(result);
+	if (table == dq->tables.size()) {
+		dq->tables.push_back(ntt);
+	}
+	defer_item item;
+	item.ptrs.src = dev_u64_nodefer(operand);
+	item.ptrs.dst = dev_u64_nodefer(result);
+	item.table = table;
 	dq->inverse = inverse;
-	dq->ntt = ntt;
-	dq->items.push_back(ent);
+	dq->log2n = ntt->log2n;
+	dq->items.push_back(item);
 	dq->reads.insert(rd);
 	dq->writes.insert(wr);
 	return true;
