@@ -31,6 +31,9 @@ struct device_ctx {
 	void *stream_h2d;    /* vkhel_vector_upload: host -> device copy engine */
 	void *stream_d2h;    /* vkhel_vector_download: device -> host copy engine */
 	void *ev_scratch;    /* cudaEvent_t used to fork from the compute stream */
+	void *stream_aux;    /* second compute stream for sliced transforms */
+	void *ev_aux;        /* fork/join event of the sliced transforms */
+	void *launch_stream; /* non-NULL while kernels go to stream_aux */
 	/* Every use of a vector on the compute stream takes the next serial
 	 * number; fork_ev[i] was recorded on the compute stream when the serial
 	 * stood at fork_serial[i], so it covers every use up to that number.  A

@@ -112,9 +112,13 @@ extern "C" void device_ctx_init(struct device_ctx *dev, int device) {
 	dev->stream_h2d = copy_stream;
 	CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
 	dev->stream_d2h = copy_stream;
+	CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+	dev->stream_aux = copy_stream;
 	cudaEvent_t fork_event;
 	CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
 	dev->ev_scratch = fork_event;
+	CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+	dev->ev_aux = fork_event;
 	for (int i = 0; i < VKHEL_FORK_EVENTS; i++) {
 		CUDA_CHECK(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
 		dev->fork_ev[i] = fork_event;
@@ -148,7 +152,9 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	CUDA_CHECK(cudaStreamSynchronize(stream));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_d2h));
+	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_aux));
 	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_scratch));
+	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_aux));
 	for (int i = 0; i < VKHEL_FORK_EVENTS; i++) {
 		CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->fork_ev[i]));
 	}

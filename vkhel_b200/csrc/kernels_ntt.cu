@@ -282,6 +282,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef FAST_PDL
 #define FAST_PDL 1
 #endif
+#ifndef VKHEL_DEFAULT_SLICE_MIB
+#define VKHEL_DEFAULT_SLICE_MIB 32
+#endif
 #ifndef FAST_PDL_EARLY
 #define FAST_PDL_EARLY 0
 #endif
@@ -302,6 +305,10 @@ struct fast_pass {
 	 * pass of a transform reads what the first one wrote (tab[i].dst) */
 	const ntt_ptrs *tab;
 	unsigned tab_second;
+	/* limb slice: this launch covers limbs [limb0, limb0 + limbs) of vectors
+	 * laid out [batch][limbs_total][n]; descs already points at limb0.  The
+	 * whole vector: limb0 = 0, limbs_total = limbs. */
+	unsigned limbs_total, limb0;
 };
 
 /* padded position of tile element i in a warp-group's exchange buffer: 4 words
@@ -331,6 +338,13 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 #endif
 }
 
+/* the stream the fast kernels go to: the context's, or the auxiliary one
+ * while launch_ntt alternates slices between the two */
+static inline cudaStream_t launch_stream(struct vkhel_ctx *ctx) {
+	return ctx->dev.launch_stream ? (cudaStream_t) ctx->dev.launch_stream
+		: ctx_stream(ctx);
+}
+
 template <class... KArgs, class... Args>
 static void launch_fast(struct vkhel_ctx *ctx, void (*kernel)(KArgs...),
 		unsigned grid, unsigned block, size_t smem, Args... args) {
@@ -338,7 +352,7 @@ static void launch_fast(struct vkhel_ctx *ctx, void (*kernel)(KArgs...),
 	cfg.gridDim = dim3(grid);
 	cfg.blockDim = dim3(block);
 	cfg.dynamicSmemBytes = smem;
-	cfg.stream = ctx_stream(ctx);
+	cfg.stream = launch_stream(ctx);
 	cudaLaunchAttribute attr;
 	attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr.val.programmaticStreamSerializationAllowed = FAST_PDL;
@@ -497,7 +511,7 @@ ntt_rows_kernel(const fast_pass p) {
 			const unsigned nh = nidx & (hgroup - 1);
 			const unsigned nbl = (nidx >> p.hgroup_log2) * NP;
 			if (nidx < nitems && nbl < nb && (t << 4) < (1 << K)) {
-				const u64 npoly = (b0 + nbl) * p.limbs + limb;
+				const u64 npoly = (b0 + nbl) * p.limbs_total + p.limb0 + limb;
 				const u64 *np_ = p.src + (npoly << L) + ((u64) (H0 + nh) << K)
 					+ (t << 4);
 				asm volatile("prefetch.global.L2 [%0];" :: "l"(np_));
@@ -508,7 +522,7 @@ ntt_rows_kernel(const fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			const unsigned bl = bg * NP + pp;
 			active[pp] = idx < nitems && bl < nb;
-			const u64 poly = (b0 + bl) * p.limbs + limb;
+			const u64 poly = (b0 + bl) * p.limbs_total + p.limb0 + limb;
 			const u64 *sp;
 			if (IND) {
 				off[pp] = (u64) (H0 + h) << K;
@@ -862,9 +876,14 @@ ntt_cols_kernel(const fast_pass p) {
 	const u64 cg = blk & (((u64) 1 << cgroups_log2) - 1);
 	blk >>= cgroups_log2;
 	const u64 H = blk & (((u64) 1 << s0) - 1);
-	const u64 poly = blk >> s0;
+	const u64 lpoly = blk >> s0;
 
-	const limb_desc &d = p.descs[poly % p.limbs];
+	/* blk counts the polynomials of this launch: (batch entry, limb of the
+	 * slice) -> position in the [batch][limbs_total] layout */
+	const unsigned pb = (unsigned) lpoly / p.limbs;   /* grid below 2^31 */
+	const unsigned pl = (unsigned) lpoly - pb * p.limbs;
+	const u64 poly = (u64) pb * p.limbs_total + p.limb0 + pl;
+	const limb_desc &d = p.descs[pl];
 	const u64 q = d.q, bq = APX ? 3 * q : 2 * q;   /* butterfly bound */
 
 	const int c = (threadIdx.x & ((1 << C::cthreads_log2) - 1)) * NP;
@@ -1147,11 +1166,14 @@ static fast_plan plan_fast(unsigned log2n) {
 template <bool INV, bool APX>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
-		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL) {
+		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL,
+		unsigned limbs_total = 0, unsigned limb0 = 0) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
 	p.tab = tab;
 	p.tab_second = 0;
+	p.limbs_total = limbs_total ? limbs_total : (unsigned) limbs;
+	p.limb0 = limb0;
 	VK_REQUIRE(!tab || !pl.lead, "internal: indirect batch of n > 2^18");
 	p.src2 = NULL;
 	p.descs = descs;
@@ -1270,6 +1292,8 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	fast_pass p;
 	p.tab = NULL;
 	p.tab_second = 0;
+	p.limbs_total = (unsigned) limbs;
+	p.limb0 = 0;
 	p.src2 = NULL;
 	p.descs = descs;
 	p.limbs = (unsigned) limbs;
@@ -1341,6 +1365,99 @@ static bool use_approx(uint64_t q_max, unsigned log2n) {
 	return !force_exact && q_max < 0xffffffffffffffffull / 6 && log2n <= 18;
 }
 
+static void run_fast_any(struct vkhel_ctx *ctx, bool inverse, bool apx,
+		const u64 *src, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, unsigned limbs_total, unsigned limb0) {
+	if (apx) {
+		if (inverse) run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n, NULL, NULL, limbs_total, limb0);
+		else run_fast<false, true>(ctx, src, dst, descs, limbs, polys, log2n, NULL, NULL, limbs_total, limb0);
+	} else {
+		if (inverse) run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n, NULL, NULL, limbs_total, limb0);
+		else run_fast<false, false>(ctx, src, dst, descs, limbs, polys, log2n, NULL, NULL, limbs_total, limb0);
+	}
+}
+
+/* ---- L2-resident intermediate -------------------------------------------------------
+ * A two-pass transform writes the whole batch between its passes and reads it
+ * back: 32n bytes of HBM traffic per transform for 16n algorithmic.  When the
+ * batch is larger than L2 it is therefore cut into slices small enough that a
+ * slice written by the first pass is still in L2 when the second pass reads
+ * it: by limb ranges for an RNS batch (a row-pass CTA shares its twiddles over
+ * the batch entries of one limb, so whole limbs stay together), by batch
+ * ranges for a single modulus.  The slices alternate between the context's
+ * stream and an auxiliary one, so that the ragged end of one slice's kernels
+ * overlaps the next slice instead of leaving SMs idle.  $VKHEL_SLICE_MIB sets
+ * the slice size for both cases (0 turns slicing off). */
+static size_t slice_bytes_setting(bool by_limb) {
+	static long mib = -2;
+	if (mib == -2) {
+		const char *env = getenv("VKHEL_SLICE_MIB");
+		mib = env && *env ? atol(env) : -1;
+	}
+	if (mib >= 0) {
+		return (size_t) mib << 20;
+	}
+	/* measured on B200: slicing an RNS batch by limbs costs
+	 * no time (n = 2^16, 32 limbs x 16: 1.54 M NTT/s either way) and takes
+	 * the DRAM traffic from 2.0x to 1.1x the algorithmic bytes; slicing a
+	 * single-modulus batch by batch ranges costs 1-3 %, so it is opt-in */
+	return by_limb ? (size_t) VKHEL_DEFAULT_SLICE_MIB << 20 : 0;
+}
+
+static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
+		const u64 *src, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n) {
+	const bool by_limb = limbs > 1;
+	const size_t slice = slice_bytes_setting(by_limb);
+	const fast_plan pl = plan_fast(log2n);
+	const size_t poly_bytes = sizeof(u64) << log2n;
+	const size_t total = polys * poly_bytes;
+	if (!slice || !pl.kcol || pl.lead || total < 3 * slice
+			|| total <= ctx->dev.l2_bytes) {
+		return false;   /* single pass, or the batch fits in L2 anyway */
+	}
+	const uint64_t batch = polys / limbs;
+	/* units: limbs (all batch entries of each) or, for one modulus, batch
+	 * entries */
+	const uint64_t units = by_limb ? limbs : batch;
+	const size_t unit_bytes = (by_limb ? batch : 1) * poly_bytes;
+	uint64_t per = slice / unit_bytes;
+	if (per < 1) {
+		per = 1;
+	}
+	if (!by_limb && per < 16 && per < units) {
+		per = 16 < units ? 16 : units;   /* keep the twiddle sharing of the row pass */
+	}
+	const uint64_t nslices = (units + per - 1) / per;
+	if (nslices < 2) {
+		return false;
+	}
+	cudaStream_t main_stream = ctx_stream(ctx);
+	cudaStream_t aux = (cudaStream_t) ctx->dev.stream_aux;
+	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_aux;
+	/* fork: the auxiliary stream continues from here */
+	CUDA_CHECK(cudaEventRecord(ev, main_stream));
+	CUDA_CHECK(cudaStreamWaitEvent(aux, ev, 0));
+	for (uint64_t i = 0; i < nslices; i++) {
+		const uint64_t u0 = i * per;
+		const uint64_t cnt = units - u0 < per ? units - u0 : per;
+		ctx->dev.launch_stream = (i & 1) ? (void *) aux : NULL;
+		if (by_limb) {
+			run_fast_any(ctx, inverse, apx, src, dst, descs + u0, cnt,
+					cnt * batch, log2n, (unsigned) limbs, (unsigned) u0);
+		} else {
+			const size_t off = (size_t) u0 << log2n;
+			run_fast_any(ctx, inverse, apx, src + off, dst + off, descs, 1,
+					cnt, log2n, 0, 0);
+		}
+	}
+	ctx->dev.launch_stream = NULL;
+	/* join */
+	CUDA_CHECK(cudaEventRecord(ev, aux));
+	CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
+	return true;
+}
+
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, uint64_t q_max) {
@@ -1350,13 +1467,13 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 	const bool strict = q_max >= (1ull << 62);
 	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
 	if (!strict && log2n >= 3 && !force_generic) {
-		if (use_approx(q_max, log2n)) {
-			if (inverse) run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n);
-			else run_fast<false, true>(ctx, src, dst, descs, limbs, polys, log2n);
-		} else {
-			if (inverse) run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n);
-			else run_fast<false, false>(ctx, src, dst, descs, limbs, polys, log2n);
+		const bool apx = use_approx(q_max, log2n);
+		if (run_fast_sliced(ctx, inverse, apx, src, dst, descs, limbs, polys,
+					log2n)) {
+			return;
 		}
+		run_fast_any(ctx, inverse, apx, src, dst, descs, limbs, polys, log2n,
+				0, 0);
 		return;
 	}
 	if (inverse) {
