@@ -42,10 +42,23 @@ METRIC = "64-bit NTTs/sec at n=2^16"
 # measured per-GPU integer peaks (profiles/r01_bfly_bench.txt)
 BFLY_PEAK_G = 1038.0         # lazy Harvey butterflies/s, best compiled form (v19)
 BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
-# DRAM bytes of one step (4 launches) from the ncu --set full capture
-# profiles/r01_ntt_ncu_full.txt: sum of dram__bytes_read + dram__bytes_write
-NCU_TRAFFIC_BYTES_PER_STEP = int((268.604 + 220.467 + 303.027 + 212.954
-                                  + 302.851 + 215.881 + 269.238 + 215.945) * 1e6)
+# DRAM bytes of one step as measured by ncu (profiles/r01_ntt_traffic.json,
+# made by tools/ncu_traffic.py from a --cache-control none launch list of this
+# very command); the constant is the value of that file at commit time
+NCU_TRAFFIC_BYTES_PER_STEP = 1180000000
+NCU_TRAFFIC_SOURCE = ("ncu --cache-control none --metrics dram__bytes_*, "
+                      "profiles/r01_ntt_traffic.json")
+
+
+def ncu_traffic():
+    path = os.path.join(ROOT, "profiles", "r01_ntt_traffic.json")
+    try:
+        with open(path) as f:
+            return int(json.load(f)["bytes_per_step"]), NCU_TRAFFIC_SOURCE
+    except (OSError, KeyError, ValueError):
+        return NCU_TRAFFIC_BYTES_PER_STEP, NCU_TRAFFIC_SOURCE
+
+
 WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
             "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
             "step = forward + inverse of the whole batch")
@@ -418,10 +431,10 @@ def run_native_arm(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_STEP,
-                "traffic_source": "ncu --set full, profiles/"
-                                  "r01_ntt_ncu_full.txt (two passes per "
-                                  "transform: ~2x the algorithmic bytes)",
+                "traffic": ncu_traffic()[0],
+                "traffic_source": ncu_traffic()[1] + " (two passes per "
+                                  "transform, the intermediate stays in L2: "
+                                  "limb slices on two streams)",
                 "peak_source": peak_src,
                 "kernel": "whole step (forward + inverse NTT, all passes)",
                 "algorithmic_bytes_per_step": algo_bytes,
