@@ -233,6 +233,32 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_near_gpu(device):
+    """Multi-rank runs: keep this rank (and therefore its pinned host buffers,
+    which are first-touched by it) on the NUMA node its GPU hangs off, so that
+    the ranks' host <-> device copies do not all cross one inter-socket link.
+    Best effort; returns what was done for the JSON line."""
+    try:
+        bus = subprocess.check_output(
+            ["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id",
+             "--format=csv,noheader"], text=True).strip().lower()
+        dom, rest = bus.split(":", 1)
+        sysdir = "/sys/bus/pci/devices/%s:%s" % (dom[-4:], rest)
+        with open(sysdir + "/numa_node") as f:
+            node = int(f.read())
+        with open(sysdir + "/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, subprocess.SubprocessError) as err:
+        return {"error": str(err)[:80]}
+
+
 # ---- GPU arm -------------------------------------------------------------------------
 def run_native_arm(args):
     import vkhel_b200 as vk
@@ -252,6 +278,7 @@ def run_native_arm(args):
     if vk.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; vkhel has no CPU path "
                          "(use --impl reference for the CPU baseline)")
+    numa = bind_near_gpu(local_rank) if world > 1 else None
 
     def barrier():
         if dist is not None:
@@ -406,6 +433,7 @@ def run_native_arm(args):
                 "no collective" % world,
                 "l2": "working set 512 MiB per step > 126 MB L2, no flush",
                 "round_trip_exact": ok,
+                "host_numa_binding": numa,
             },
             "e2e": {"value": e2e_value, "unit": "NTT/s",
                     "h2d_bytes_per_step": POLYS * N * 8,
