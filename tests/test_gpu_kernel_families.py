@@ -4,8 +4,12 @@ By default q < 2^64/6 runs the approximate-quotient butterflies, larger
 q < 2^62 the exact-quotient ones and q >= 2^62 (or n < 8) the generic kernel.
 The environment switches $VKHEL_EXACT_QUOTIENT and $VKHEL_FORCE_GENERIC force
 the slower families for every modulus, $VKHEL_POLYMUL_UNFUSED the polynomial
-product as separate transforms; they are read once per process, so the parity
-tests are re-run in child processes."""
+product as separate transforms, $VKHEL_NO_DEFER immediate launches of the
+single-vector transforms, $VKHEL_SINGLE_MAX_LOG2N the sizes that take the
+single-pass kernel (8 = none, 12 = one more than the default) and
+$VKHEL_SLICE_MIB=0.0625 cuts every two-pass batch above 192 KiB into slices on two
+streams; they are read once per process, so the parity tests are re-run in
+child processes."""
 import os
 import subprocess
 import sys
@@ -23,10 +27,14 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
 @pytest.mark.parametrize("switch", ["VKHEL_EXACT_QUOTIENT",
                                     "VKHEL_FORCE_GENERIC",
                                     "VKHEL_POLYMUL_UNFUSED",
-                                    "VKHEL_NO_DEFER"])
+                                    "VKHEL_NO_DEFER",
+                                    "VKHEL_SINGLE_MAX_LOG2N=8",
+                                    "VKHEL_SINGLE_MAX_LOG2N=12",
+                                    "VKHEL_SLICE_MIB=0.0625"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)
-    env[switch] = "1"
+    name, _, value = switch.partition("=")
+    env[name] = value or "1"
     res = subprocess.run(
         [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
          "-p", "no:cacheprovider", "-k", SELECT,

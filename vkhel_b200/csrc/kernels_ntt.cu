@@ -837,6 +837,156 @@ ntt_rows_polymul_kernel(const fast_pass p) {
 	}
 }
 
+/* ---- single pass for 2^9 <= n <= 2^11 ---------------------------------------------------
+ * Two passes move 32n bytes per transform; at n = 2^9 .. 2^12 the batched
+ * transform then runs at 4.3-4.6 TB/s of real traffic, i.e. it is bound by HBM,
+ * not by the butterflies.  A polynomial of up to 4096 coefficients fits one
+ * CTA: 2^(K-3) threads hold 8 coefficients each and run all K = log2 n stages,
+ * exchanging through (padded) shared memory between rounds.  The CTA stages
+ * the whole twiddle table of its limb once (TMA, one copy per level) and
+ * reuses it over `bchunk` batch entries.  16n bytes per transform, one launch.
+ * Measured on B200 at 2^27 coefficients, forward / inverse, against the
+ * two-pass split: n = 2^9 0.74 / 0.76 ms (0.99 / 0.97), 2^10 0.81 / 0.78
+ * (0.93 / 0.94), 2^11 0.97 / 0.89 (1.00 / 1.00), 2^12 1.18 / 1.20 (1.00 /
+ * 1.11: 512 threads and 96 KB per CTA, two CTAs per SM -- slower, so the
+ * default stops at 2^11; $VKHEL_SINGLE_MAX_LOG2N moves the limit, 8 = off). */
+#ifndef SINGLE_MAX_LOG2N
+#define SINGLE_MAX_LOG2N 11
+#endif
+
+template <bool INV, int K, bool APX, bool IND>
+__global__ void __launch_bounds__(1 << (K - 3), (1024 >> (K - 3)) > 16 ? 16 : (1024 >> (K - 3)))
+ntt_single_kernel(const fast_pass p) {
+	using G = tile_geom<K>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;           /* [2^K] */
+	u64 *sm_x = (u64 *) (sm_tw + (1 << K));                /* xpad(2^K) words */
+
+	/* blockIdx.x -> (batch chunk, limb) */
+	const unsigned limb = blockIdx.x % p.limbs;
+	const unsigned bc = blockIdx.x / p.limbs;
+	const u64 batch = p.polys / p.limbs;
+	const u64 b0 = (u64) bc * p.bchunk;
+	const unsigned nb = (unsigned) (batch - b0 < p.bchunk ? batch - b0 : p.bchunk);
+
+	const limb_desc &d = p.descs[limb];
+	const u64 q = d.q, bq = APX ? 3 * q : 2 * q;
+	__shared__ __align__(8) u64 tw_bar;
+	if (threadIdx.x == 0) {
+		mbar_init(&tw_bar, 1);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << K) : 0), 0, 0, 1,
+				&tw_bar);
+	}
+	pdl_wait();
+
+	const int t = threadIdx.x;
+	constexpr int first = INV ? G::rounds - 1 : 0;
+	constexpr int last = INV ? 0 : G::rounds - 1;
+	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
+	if (INV) {
+		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
+		fold_b = make_ulonglong2(d.inv_w1n, d.inv_w1n_shoup);
+	}
+	const int tb_first = G::tbase(first, t), tb_last = G::tbase(last, t);
+	bool tw_ready = false;
+
+	for (unsigned bl = 0; bl < nb; bl++) {
+		const u64 poly = (b0 + bl) * p.limbs_total + p.limb0 + limb;
+		const u64 *sp;
+		u64 *dp;
+		if (IND) {
+			const ntt_ptrs ent = p.tab[poly];
+			sp = ent.src;
+			dp = ent.dst;
+		} else {
+			sp = p.src + (poly << K);
+			dp = p.dst + (poly << K);
+		}
+		u64 x[1][8];
+		if (G::eoff(first, 1) == 1) {
+#pragma unroll
+			for (int e = 0; e < 8; e += 2) {
+				const ulonglong2 v =
+					*(const ulonglong2 *) (sp + tb_first + G::eoff(first, e));
+				x[0][e] = v.x;
+				x[0][e + 1] = v.y;
+			}
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				x[0][e] = sp[tb_first + G::eoff(first, e)];
+			}
+		}
+		if (!tw_ready) {
+			mbar_wait(&tw_bar, 0);
+			tw_ready = true;
+		}
+#pragma unroll
+		for (int rr = 0; rr < G::rounds; rr++) {
+			const int r = INV ? G::rounds - 1 - rr : rr;
+			if (rr > 0) {
+				const int prev = INV ? r + 1 : r - 1;
+				u64 *xw = sm_x + xpad(G::tbase(prev, t));
+				if (G::eoff(prev, 1) == 1) {
+#pragma unroll
+					for (int e = 0; e < 8; e += 2) {
+						*(ulonglong2 *) (xw + xpad(G::eoff(prev, e))) =
+							make_ulonglong2(x[0][e], x[0][e + 1]);
+					}
+				} else {
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						xw[xpad(G::eoff(prev, e))] = x[0][e];
+					}
+				}
+				__syncthreads();
+				const u64 *xr = sm_x + xpad(G::tbase(r, t));
+				if (G::eoff(r, 1) == 1) {
+#pragma unroll
+					for (int e = 0; e < 8; e += 2) {
+						const ulonglong2 v =
+							*(const ulonglong2 *) (xr + xpad(G::eoff(r, e)));
+						x[0][e] = v.x;
+						x[0][e + 1] = v.y;
+					}
+				} else {
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						x[0][e] = xr[xpad(G::eoff(r, e))];
+					}
+				}
+				/* the next exchange writes exactly the words this thread has
+				 * just read: no second barrier */
+			}
+			tile_round<K, INV, INV, 1, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
+		}
+		if (bl + 1 == nb) {
+			pdl_launch_dependents();   /* only this CTA's last stores remain */
+		} else {
+			__syncthreads();           /* the next entry reuses the buffer */
+		}
+#pragma unroll
+		for (int e = 0; e < 8; e++) {
+			x[0][e] = tile_canon<INV, APX>(x[0][e], q, bq);
+		}
+		if (G::eoff(last, 1) == 1) {
+#pragma unroll
+			for (int e = 0; e < 8; e += 2) {
+				*(ulonglong2 *) (dp + tb_last + G::eoff(last, e)) =
+					make_ulonglong2(x[0][e], x[0][e + 1]);
+			}
+		} else {
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				dp[tb_last + G::eoff(last, e)] = x[0][e];
+			}
+		}
+	}
+}
+
 /* Column pass.  CTA = (poly, H, column group): one tile group of 2^K rows at
  * stride 2^(L-s0-K) by 2^CL adjacent columns.  thread = (row group, NP adjacent
  * columns), lanes along the columns: every global access is a run of 2^CL * 8
@@ -1143,6 +1293,67 @@ static void run_cols_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
 	}
 }
 
+template <bool INV, int K, bool APX>
+static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
+	const u64 batch = p.polys / p.limbs;
+	constexpr unsigned threads = 1u << (K - 3);
+	/* batch entries per CTA: reuse the staged twiddles, but keep at least four
+	 * waves of CTAs */
+	const u64 resident = (u64) ctx->dev.sm_count * (2048 / threads > 16 ? 16 : 2048 / threads);
+	u64 bchunk = batch * p.limbs / (4 * resident);
+	if (bchunk > 16) {
+		bchunk = 16;
+	}
+	if (bchunk < 1) {
+		bchunk = 1;
+	}
+	p.bchunk = (unsigned) bchunk;
+	const u64 blocks = ((batch + bchunk - 1) / bchunk) * p.limbs;
+	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
+	const size_t smem = (sizeof(ulonglong2) << K)
+		+ sizeof(u64) * (size_t) (xpad(1 << K) + 4);
+	if (p.tab) {
+		if (smem > 48 * 1024) {
+			CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, true>,
+						cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		}
+		launch_fast(ctx, ntt_single_kernel<INV, K, APX, true>, (unsigned) blocks,
+				threads, smem, p);
+		return;
+	}
+	if (smem > 48 * 1024) {
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, false>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
+	launch_fast(ctx, ntt_single_kernel<INV, K, APX, false>, (unsigned) blocks,
+			threads, smem, p);
+}
+
+template <bool INV, bool APX>
+static void run_single_k(struct vkhel_ctx *ctx, const fast_pass &p, unsigned k) {
+	switch (k) {
+	case 9: run_single<INV, 9, APX>(ctx, p); break;
+	case 10: run_single<INV, 10, APX>(ctx, p); break;
+	case 11: run_single<INV, 11, APX>(ctx, p); break;
+	case 12: run_single<INV, 12, APX>(ctx, p); break;
+	default: VK_DIE("internal: single pass of %u stages", k);
+	}
+}
+
+/* n in [2^9, 2^single_max]: one pass ($VKHEL_SINGLE_MAX_LOG2N, default 12; 8
+ * disables it) */
+static unsigned single_max_log2n() {
+	static int v = -1;
+	if (v < 0) {
+		const char *env = getenv("VKHEL_SINGLE_MAX_LOG2N");
+		v = env && *env ? atoi(env) : SINGLE_MAX_LOG2N;
+		if (v > 12) {
+			v = 12;
+		}
+	}
+	return (unsigned) v;
+}
+
 /* stage split of the fast path: [lead (generic, strided)] [col] [row] */
 struct fast_plan {
 	unsigned lead, kcol, krow;
@@ -1182,6 +1393,14 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	p.polys = polys;
 	p.hgroup_log2 = 0;
 	p.bchunk = 1;
+
+	if (!src2 && log2n >= 9 && log2n <= single_max_log2n()) {
+		p.src = src;
+		p.dst = dst;
+		p.s0 = 0;
+		run_single_k<INV, APX>(ctx, p, log2n);
+		return;
+	}
 
 	gen_pass lead;
 	lead.descs = descs;
@@ -1387,15 +1606,17 @@ static void run_fast_any(struct vkhel_ctx *ctx, bool inverse, bool apx,
  * ranges for a single modulus.  The slices alternate between the context's
  * stream and an auxiliary one, so that the ragged end of one slice's kernels
  * overlaps the next slice instead of leaving SMs idle.  $VKHEL_SLICE_MIB sets
- * the slice size for both cases (0 turns slicing off). */
-static size_t slice_bytes_setting(bool by_limb) {
-	static long mib = -2;
+ * the slice size for both cases (0 turns slicing off; a set value also slices
+ * batches that would fit in L2, which is what the tests use). */
+static size_t slice_bytes_setting(bool by_limb, bool *forced) {
+	static double mib = -2;
 	if (mib == -2) {
 		const char *env = getenv("VKHEL_SLICE_MIB");
-		mib = env && *env ? atol(env) : -1;
+		mib = env && *env ? atof(env) : -1;
 	}
+	*forced = mib >= 0;
 	if (mib >= 0) {
-		return (size_t) mib << 20;
+		return (size_t) (mib * 1048576.0);
 	}
 	/* measured on B200: slicing an RNS batch by limbs costs
 	 * no time (n = 2^16, 32 limbs x 16: 1.54 M NTT/s either way) and takes
@@ -1408,12 +1629,14 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		const u64 *src, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n) {
 	const bool by_limb = limbs > 1;
-	const size_t slice = slice_bytes_setting(by_limb);
+	bool forced;
+	const size_t slice = slice_bytes_setting(by_limb, &forced);
 	const fast_plan pl = plan_fast(log2n);
 	const size_t poly_bytes = sizeof(u64) << log2n;
 	const size_t total = polys * poly_bytes;
 	if (!slice || !pl.kcol || pl.lead || total < 3 * slice
-			|| total <= ctx->dev.l2_bytes) {
+			|| (log2n >= 9 && log2n <= single_max_log2n())
+			|| (!forced && total <= ctx->dev.l2_bytes)) {
 		return false;   /* single pass, or the batch fits in L2 anyway */
 	}
 	const uint64_t batch = polys / limbs;
