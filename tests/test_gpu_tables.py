@@ -71,6 +71,15 @@ def test_rns_basis_generated_on_device(ctx):
     ctx.forward_transform_rns(a, a, tabs, batch)
     assert np.array_equal(a.to_host(),
                           oracle.forward_batch(x, oras, threads=4))
+    # the inverse's column pass reads the scaled top of the inverse table,
+    # which for device-generated tables is appended when the mirror is adopted
+    ctx.inverse_transform_rns(a, a, tabs, batch)
+    assert np.array_equal(a.to_host(), x)
+    y = ctx.from_host(x)
+    ctx.inverse_transform_rns(y, y, tabs, batch)
+    assert np.array_equal(y.to_host(),
+                          oracle.inverse_batch(x, oras, threads=4))
+    y.destroy()
     a.destroy()
     for t in tabs:
         t.destroy()

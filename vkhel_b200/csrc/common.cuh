@@ -38,7 +38,19 @@ static inline cudaStream_t ctx_stream(const struct vkhel_ctx *ctx) {
 /* ---- device view of one table (one RNS limb) -------------------------------
  * tw[k]     = (root[k],     floor(root[k]*2^64/q))      k in [0,n)
  * tw[n + k] = (inv_root[k], floor(inv_root[k]*2^64/q))
- * in the reference's bit-reversed order (stage m uses the slice [m, 2m)). */
+ * in the reference's bit-reversed order (stage m uses the slice [m, 2m)).
+ * tw[2n + k] = the pair of inv_root[k] * n^-1 mod q, k in [0, scaled_tw_pairs(n)):
+ * the top of the inverse twiddle heap with the inverse transform's n^-1 factor
+ * multiplied in (column pass of the inverse, kernels_ntt.cu). */
+#define SCALED_TW_MAX_LOG2 10
+static inline uint64_t scaled_tw_pairs(uint64_t n) {
+	return n < (1ull << SCALED_TW_MAX_LOG2) ? n : (1ull << SCALED_TW_MAX_LOG2);
+}
+/* bytes of the (w, w') pairs of one device mirror */
+static inline size_t mirror_pair_bytes(uint64_t n) {
+	return (size_t) (2 * n + scaled_tw_pairs(n)) * sizeof(ulonglong2);
+}
+
 struct limb_desc {
 	const ulonglong2 *tw;
 	u64 q;

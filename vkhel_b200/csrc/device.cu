@@ -353,9 +353,21 @@ extern "C" void vkhel_host_free(void *ptr) {
 }
 
 /* ---- NTT table device mirrors -------------------------------------------------
- * Layout of one mirror: [limb_desc (64 B)][2n pairs of (w, w')].  The tables
- * object has no context (reference src/ntt_tables.c:65-87), so the mirror is
- * a plain cudaMalloc keyed by device ordinal and freed in tables_destroy. */
+ * Layout of one mirror: [limb_desc (64 B)][2n pairs of (w, w')][the first
+ * scaled_tw_pairs(n) inverse pairs times n^-1].  The tables object has no
+ * context (reference src/ntt_tables.c:65-87), so the mirror is keyed by device
+ * ordinal and freed in tables_destroy. */
+/* inv_root[k] * n^-1 and its Shoup companion, k < scaled_tw_pairs(n) */
+static void fill_scaled_pairs(const struct vkhel_ntt_tables *ntt,
+		ulonglong2 *out) {
+	const uint64_t count = scaled_tw_pairs(ntt->n);
+	for (uint64_t k = 0; k < count; k++) {
+		const uint64_t w = nt_multiply_mod(ntt->inv_roots_of_unity[k],
+				ntt->inv_n, ntt->q, 0);
+		out[k] = make_ulonglong2(w, nt_compute_barrett_factor(w, ntt->q, 64));
+	}
+}
+
 static void fill_desc(const struct vkhel_ntt_tables *ntt, limb_desc *desc,
 		const ulonglong2 *dev_pairs) {
 	const uint64_t n = ntt->n;
@@ -408,8 +420,7 @@ static void *ensure_mirror(struct vkhel_ctx *ctx,
 	VK_REQUIRE(ntt->q < (1ull << 63),
 			"NTT modulus must be below 2^63 (as in the reference, whose "
 			"nt_inverse_mod works in int64_t)");
-	const size_t pair_bytes = 2 * ntt->n * sizeof(ulonglong2);
-	const size_t bytes = sizeof(limb_desc) + pair_bytes;
+	const size_t bytes = sizeof(limb_desc) + mirror_pair_bytes(ntt->n);
 	char *dev_buf = (char *) ntt_tables_mirror_alloc(ctx, bytes);
 	char *host_buf = (char *) malloc(bytes);
 	VK_REQUIRE(host_buf, "out of host memory");
@@ -422,6 +433,7 @@ static void *ensure_mirror(struct vkhel_ctx *ctx,
 		pairs[ntt->n + k] = make_ulonglong2(ntt->inv_roots_of_unity[k],
 				ntt->inv_roots_barrett_factors[k]);
 	}
+	fill_scaled_pairs(ntt, pairs + 2 * ntt->n);
 	/* on the context's stream, after the allocation; completed here so that
 	 * the host buffer can be freed right away and other contexts of this
 	 * device can use the mirror */
@@ -441,6 +453,14 @@ void ntt_tables_adopt_mirror(struct vkhel_ctx *ctx,
 	limb_desc desc;
 	fill_desc(ntt, &desc, (const ulonglong2 *) (dev_buf + sizeof(limb_desc)));
 	CUDA_CHECK(cudaMemcpyAsync(dev_buf, &desc, sizeof(desc),
+				cudaMemcpyHostToDevice, ctx_stream(ctx)));
+	/* the scaled top of the inverse heap: at most 1024 products, made here
+	 * from the host arrays the generator has already copied back */
+	ulonglong2 scaled[1 << SCALED_TW_MAX_LOG2];
+	fill_scaled_pairs(ntt, scaled);
+	CUDA_CHECK(cudaMemcpyAsync(dev_buf + sizeof(limb_desc)
+				+ 2 * ntt->n * sizeof(ulonglong2), scaled,
+				scaled_tw_pairs(ntt->n) * sizeof(ulonglong2),
 				cudaMemcpyHostToDevice, ctx_stream(ctx)));
 	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(ctx)));
 	ntt->dev_pairs[ctx->dev.device] = dev_buf;

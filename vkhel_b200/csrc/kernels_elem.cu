@@ -5,8 +5,8 @@
  * (src/kernels/X.c), which computed the Barrett constants per call.
  *
  * All of them are HBM-bound streaming kernels (24 or 16 bytes per element,
- * a few dozen integer instructions): 128-bit coalesced loads and stores, two
- * vectors in flight per thread, grid sized to whole waves of the SM count.
+ * a few dozen integer instructions): 128-bit coalesced loads and stores, four
+ * vectors in flight per thread, one CTA per contiguous chunk.
  * Each output is the canonical residue, so results are bit-identical to the
  * shaders wherever those are defined.
  */
@@ -106,40 +106,51 @@ struct op_modbytwo { /* reference elemmodbytwo.comp:19-27 */
 
 /* ---- streaming skeleton -------------------------------------------------------------
  * result may alias an operand (in-place ops), hence no __restrict__.
- * Vector body: each thread handles UNROLL 16-byte vectors per iteration, all
- * loads issued before the first use.  `len` elements; pointers 16 B aligned
- * (the scalar kernel below covers odd tails and unaligned sub-ranges). */
+ * Vector body: a CTA takes one contiguous chunk of ELEM_THREADS * elem_unroll
+ * 16-byte vectors, each thread elem_unroll of them with all loads issued
+ * before the first use, and exits.  No grid-stride loop: with as many CTAs as
+ * chunks the hardware block scheduler balances the SMs (the two dies do not
+ * stream at the same rate); a grid of one resident wave that loops was
+ * measured 4-20 % slower at 2^27 elements (elemfma 6104 against 6722 GB/s,
+ * elemgtsub 5482 against 6843).  `len` elements; pointers 16 B aligned (the
+ * scalar kernel below covers odd tails and unaligned sub-ranges). */
 #define ELEM_THREADS 256
-#define ELEM_UNROLL 4
+/* vectors per thread: 4, except for the full product (64 registers at 4, i.e.
+ * half occupancy; measured 7094 GB/s with 2 against 6652 with 4, while
+ * elemfma loses with 2: 6521 against 7031) */
+template <class Op> struct elem_unroll { static constexpr int value = 4; };
+template <> struct elem_unroll<op_mul> { static constexpr int value = 2; };
 
 template <bool TWO_INPUTS, class Op>
 __global__ void __launch_bounds__(ELEM_THREADS)
 elem_vec_kernel(const ulonglong2 *a,
 		const ulonglong2 *b, ulonglong2 *out,
 		u64 nvec, const Op op) {
-	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
-	u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x;
-	for (; i + (ELEM_UNROLL - 1) * stride < nvec; i += ELEM_UNROLL * stride) {
+	constexpr int ELEM_UNROLL = elem_unroll<Op>::value;
+	const u64 i = (u64) blockIdx.x * (ELEM_THREADS * ELEM_UNROLL) + threadIdx.x;
+	if (i + (ELEM_UNROLL - 1) * ELEM_THREADS < nvec) {
 		ulonglong2 va[ELEM_UNROLL], vb[ELEM_UNROLL];
 #pragma unroll
 		for (int u = 0; u < ELEM_UNROLL; u++) {
-			va[u] = a[i + u * stride];
+			va[u] = a[i + u * ELEM_THREADS];
 			if (TWO_INPUTS) {
-				vb[u] = b[i + u * stride];
+				vb[u] = b[i + u * ELEM_THREADS];
 			} else {
 				vb[u] = make_ulonglong2(0, 0);
 			}
 		}
 #pragma unroll
 		for (int u = 0; u < ELEM_UNROLL; u++) {
-			out[i + u * stride] = make_ulonglong2(op(va[u].x, vb[u].x),
+			out[i + u * ELEM_THREADS] = make_ulonglong2(op(va[u].x, vb[u].x),
 					op(va[u].y, vb[u].y));
 		}
+		return;
 	}
-	for (; i < nvec; i += stride) {
-		const ulonglong2 va = a[i];
-		const ulonglong2 vb = TWO_INPUTS ? b[i] : make_ulonglong2(0, 0);
-		out[i] = make_ulonglong2(op(va.x, vb.x), op(va.y, vb.y));
+	/* the last, partial chunk */
+	for (u64 j = i; j < nvec; j += ELEM_THREADS) {
+		const ulonglong2 va = a[j];
+		const ulonglong2 vb = TWO_INPUTS ? b[j] : make_ulonglong2(0, 0);
+		out[j] = make_ulonglong2(op(va.x, vb.x), op(va.y, vb.y));
 	}
 }
 
@@ -147,19 +158,17 @@ template <bool TWO_INPUTS, class Op>
 __global__ void __launch_bounds__(ELEM_THREADS)
 elem_scalar_kernel(const u64 *a, const u64 *b, u64 *out, u64 len,
 		const Op op) {
-	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
-	for (u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x; i < len;
-			i += stride) {
+	const u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x;
+	if (i < len) {
 		out[i] = op(a[i], TWO_INPUTS ? b[i] : 0);
 	}
 }
 
-static unsigned grid_for(const struct vkhel_ctx *ctx, u64 work_items,
-		unsigned per_block) {
+/* one CTA per chunk of `per_block` work items */
+static unsigned grid_for(u64 work_items, unsigned per_block) {
 	const u64 blocks = (work_items + per_block - 1) / per_block;
-	/* at most 8 resident 256-thread CTAs per SM: one full wave */
-	const u64 wave = (u64) ctx->dev.sm_count * 8;
-	return (unsigned) (blocks < wave ? (blocks ? blocks : 1) : wave);
+	VK_REQUIRE(blocks <= 0x7fffffffull, "vector too long for one launch");
+	return (unsigned) (blocks ? blocks : 1);
 }
 
 template <bool TWO_INPUTS, class Op>
@@ -175,7 +184,7 @@ static void launch_elem(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	if ((align & 15) == 0 && len >= 2) {
 		const u64 nvec = len / 2;
 		elem_vec_kernel<TWO_INPUTS, Op>
-			<<<grid_for(ctx, nvec, ELEM_THREADS * ELEM_UNROLL),
+			<<<grid_for(nvec, ELEM_THREADS * elem_unroll<Op>::value),
 				ELEM_THREADS, 0, stream>>>(
 				(const ulonglong2 *) a, (const ulonglong2 *) b,
 				(ulonglong2 *) out, nvec, op);
@@ -186,7 +195,7 @@ static void launch_elem(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	if (done < len) {
 		const u64 rest = len - done;
 		elem_scalar_kernel<TWO_INPUTS, Op>
-			<<<grid_for(ctx, rest, ELEM_THREADS), ELEM_THREADS, 0, stream>>>(
+			<<<grid_for(rest, ELEM_THREADS), ELEM_THREADS, 0, stream>>>(
 				a + done, TWO_INPUTS ? b + done : NULL, out + done, rest, op);
 		CUDA_CHECK(cudaGetLastError());
 		ctx->dev.launches++;
@@ -247,25 +256,26 @@ elemmul_rns_kernel(const ulonglong2 *a,
 		const ulonglong2 *b, ulonglong2 *out,
 		u64 nvec, unsigned log2_vec_per_poly, unsigned limbs,
 		const __grid_constant__ rns_moduli mods) {
-	const u64 stride = (u64) gridDim.x * ELEM_THREADS;
-	for (u64 i = (u64) blockIdx.x * ELEM_THREADS + threadIdx.x; i < nvec;
-			i += 2 * stride) {
-		const u64 j = i + stride;
-		const bool second = j < nvec;
-		const ulonglong2 a0 = a[i], b0 = b[i];
-		ulonglong2 a1 = make_ulonglong2(0, 0), b1 = a1;
-		if (second) {
-			a1 = a[j];
-			b1 = b[j];
-		}
-		const modulus &m0 = mods.m[(i >> log2_vec_per_poly) % limbs];
-		out[i] = make_ulonglong2(mulmod_any(a0.x, b0.x, m0),
-				mulmod_any(a0.y, b0.y, m0));
-		if (second) {
-			const modulus &m1 = mods.m[(j >> log2_vec_per_poly) % limbs];
-			out[j] = make_ulonglong2(mulmod_any(a1.x, b1.x, m1),
-					mulmod_any(a1.y, b1.y, m1));
-		}
+	/* one chunk of 2 * ELEM_THREADS vectors per CTA, as above */
+	const u64 i = (u64) blockIdx.x * (2 * ELEM_THREADS) + threadIdx.x;
+	const u64 j = i + ELEM_THREADS;
+	if (i >= nvec) {
+		return;
+	}
+	const bool second = j < nvec;
+	const ulonglong2 a0 = a[i], b0 = b[i];
+	ulonglong2 a1 = make_ulonglong2(0, 0), b1 = a1;
+	if (second) {
+		a1 = a[j];
+		b1 = b[j];
+	}
+	const modulus &m0 = mods.m[(i >> log2_vec_per_poly) % limbs];
+	out[i] = make_ulonglong2(mulmod_any(a0.x, b0.x, m0),
+			mulmod_any(a0.y, b0.y, m0));
+	if (second) {
+		const modulus &m1 = mods.m[(j >> log2_vec_per_poly) % limbs];
+		out[j] = make_ulonglong2(mulmod_any(a1.x, b1.x, m1),
+				mulmod_any(a1.y, b1.y, m1));
 	}
 }
 
@@ -288,8 +298,8 @@ void launch_elemmul_rns(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	}
 	const u64 nvec = limbs * n * batch / 2;
 	const unsigned log2_vec_per_poly = (unsigned) nt_ceil_log2(n) - 2;
-	elemmul_rns_kernel<<<grid_for(ctx, nvec, ELEM_THREADS * 2), ELEM_THREADS,
-		0, ctx_stream(ctx)>>>((const ulonglong2 *) a, (const ulonglong2 *) b,
+	elemmul_rns_kernel<<<grid_for(nvec, ELEM_THREADS * 2), ELEM_THREADS, 0,
+		ctx_stream(ctx)>>>((const ulonglong2 *) a, (const ulonglong2 *) b,
 				(ulonglong2 *) out, nvec, log2_vec_per_poly, (unsigned) limbs,
 				params);
 	CUDA_CHECK(cudaGetLastError());

@@ -345,6 +345,13 @@ static inline cudaStream_t launch_stream(struct vkhel_ctx *ctx) {
 		: ctx_stream(ctx);
 }
 
+/* Dynamic shared memory above the default 48 KiB limit needs the per-kernel
+ * opt-in; the kernels' few static bytes (their mbarriers) count towards the
+ * same limit, hence the margin. */
+static inline bool smem_needs_optin(size_t dynamic_bytes) {
+	return dynamic_bytes + 256 > 48 * 1024;
+}
+
 template <class... KArgs, class... Args>
 static void launch_fast(struct vkhel_ctx *ctx, void (*kernel)(KArgs...),
 		unsigned grid, unsigned block, size_t smem, Args... args) {
@@ -625,9 +632,11 @@ ntt_rows_kernel(const fast_pass p) {
 				}
 			}
 			if (fold) {
-				tile_round<K, INV, true, NP, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
+				tile_round<K, INV, INV ? FOLD_LAST : FOLD_NONE, NP, APX>(x, r, t,
+						twt, q, bq, fold_a, fold_b);
 			} else {
-				tile_round<K, INV, false, NP, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
+				tile_round<K, INV, FOLD_NONE, NP, APX>(x, r, t, twt, q, bq,
+						fold_a, fold_b);
 			}
 		}
 		__syncwarp();   /* the exchange buffer is reused by the next item */
@@ -713,7 +722,8 @@ __device__ __forceinline__ void rows_rounds(u64 (&x)[1][8], u64 *xb, int t,
 				}
 			}
 		}
-		tile_round<K, INV, FOLD, 1, APX>(x, r, t, twt, q, bq, fold_a, fold_b);
+		tile_round<K, INV, FOLD ? FOLD_LAST : FOLD_NONE, 1, APX>(x, r, t, twt, q,
+				bq, fold_a, fold_b);
 	}
 }
 
@@ -961,7 +971,8 @@ ntt_single_kernel(const fast_pass p) {
 				/* the next exchange writes exactly the words this thread has
 				 * just read: no second barrier */
 			}
-			tile_round<K, INV, INV, 1, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
+			tile_round<K, INV, INV ? FOLD_LAST : FOLD_NONE, 1, APX>(x, r, t,
+					sm_tw, q, bq, fold_a, fold_b);
 		}
 		if (bl + 1 == nb) {
 			pdl_launch_dependents();   /* only this CTA's last stores remain */
@@ -992,6 +1003,14 @@ ntt_single_kernel(const fast_pass p) {
  * columns), lanes along the columns: every global access is a run of 2^CL * 8
  * contiguous bytes (128-bit per thread for NP = 2) and every shared-memory
  * access is conflict-free without padding. */
+/* How the inverse column pass applies n^-1 when it holds the last stage
+ * (ntt_engine.cuh): through the scaled top of the inverse twiddle heap
+ * (FOLD_TWID, the default: n/2 fewer modular products per transform) or by
+ * multiplying both outputs of the last stage (FOLD_LAST). */
+#ifndef COLS_FOLD
+#define COLS_FOLD FOLD_TWID
+#endif
+
 template <int K, int CL, int NP>
 struct col_cfg {
 	static constexpr int cthreads_log2 = CL - (NP == 2 ? 1 : 0);
@@ -1049,14 +1068,30 @@ ntt_cols_kernel(const fast_pass p) {
 		dst_base = ent.dst;
 	}
 
+	/* the forward transform always ends in a row pass; the inverse ends here
+	 * when this pass holds stage 0.  (A one-CTA-per-polynomial single-launch
+	 * variant of this kernel, K = log2 n, was measured no faster than the
+	 * two-pass split even for a single polynomial.) */
+	const bool fold = INV && s0 == 0;
+	constexpr int FM = INV ? COLS_FOLD : FOLD_NONE;
+	static_assert(K <= SCALED_TW_MAX_LOG2, "scaled twiddles cover 2^10 nodes");
+	/* FOLD_TWID: the tile is the top of the heap (root 1); its scaled copy
+	 * lies behind the coefficients' exchange buffer */
+	const ulonglong2 *sm_tws = (const ulonglong2 *) (sm_x + ((size_t) 1 << (K + CL)));
+	const bool scaled_tw = FM == FOLD_TWID && fold;
+
 	__shared__ __align__(8) u64 tw_bar;
 	if (threadIdx.x == 0) {
-		mbar_init(&tw_bar, 1);
+		mbar_init(&tw_bar, scaled_tw ? 2 : 1);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		stage_twiddles_tma<K>(sm_tw, d.tw + (INV ? ((u64) 1 << L) : 0), s0, H, 1,
 				&tw_bar);
+		if (scaled_tw) {
+			stage_twiddles_tma<K>((ulonglong2 *) sm_tws, d.tw + ((u64) 2 << L),
+					0, 0, 1, &tw_bar);
+		}
 	}
 	pdl_wait();   /* the coefficients come from the previous kernel */
 #if FAST_PDL_EARLY
@@ -1076,12 +1111,7 @@ ntt_cols_kernel(const fast_pass p) {
 			}
 		}
 	}
-	const bool fold = INV && s0 == 0;
-	/* the forward transform always ends in a row pass; the inverse ends here
-	 * when this pass holds stage 0.  (A one-CTA-per-polynomial single-launch
-	 * variant of this kernel, K = log2 n, was measured no faster than the
-	 * two-pass split even for a single polynomial.) */
-	const bool canon = INV && s0 == 0;
+	const bool canon = fold;
 	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
 	if (fold) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
@@ -1116,9 +1146,11 @@ ntt_cols_kernel(const fast_pass p) {
 			}
 		}
 		if (fold) {
-			tile_round<K, INV, true, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
+			tile_round<K, INV, FM, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b,
+					sm_tws);
 		} else {
-			tile_round<K, INV, false, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b);
+			tile_round<K, INV, FOLD_NONE, NP, APX>(x, r, t, sm_tw, q, bq, fold_a,
+					fold_b);
 		}
 	}
 
@@ -1131,7 +1163,7 @@ ntt_cols_kernel(const fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			u64 w = x[pp][e];
 			if (canon) {
-				w = tile_canon<true, APX>(w, q, bq);
+				w = tile_canon<true, APX, FM == FOLD_NONE ? FOLD_LAST : FM>(w, q, bq);
 			}
 			((u64 *) &v)[pp] = w;
 		}
@@ -1169,7 +1201,7 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
 	if constexpr (!MUL) {
 		if (p.tab) {
-			if (smem > 48 * 1024) {
+			if (smem_needs_optin(smem)) {
 				CUDA_CHECK(cudaFuncSetAttribute(
 							ntt_rows_kernel<INV, K, NP, false, APX, true>,
 							cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1180,7 +1212,7 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 			return;
 		}
 	}
-	if (smem > 48 * 1024) {
+	if (smem_needs_optin(smem)) {
 		/* per device, and cheap: set it on every such launch */
 		CUDA_CHECK(cudaFuncSetAttribute(
 					ntt_rows_kernel<INV, K, NP, MUL, APX, false>,
@@ -1216,9 +1248,13 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 			"internal: column pass narrower than its CTA");
 	const u64 blocks = (p.polys << p.s0) << (low_bits - CL);
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
-	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL));
+	/* twiddle subtree, exchange buffer, and for the inverse's last pass the
+	 * scaled subtree (COLS_FOLD) */
+	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL))
+		+ (INV && COLS_FOLD == FOLD_TWID && p.s0 == 0
+				? sizeof(ulonglong2) << K : 0);
 	if (p.tab) {
-		if (smem > 48 * 1024) {
+		if (smem_needs_optin(smem)) {
 			CUDA_CHECK(cudaFuncSetAttribute(
 						ntt_cols_kernel<INV, K, CL, NP, APX, true>,
 						cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1228,7 +1264,7 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 				(unsigned) blocks, C::threads, smem, p);
 		return;
 	}
-	if (smem > 48 * 1024) {
+	if (smem_needs_optin(smem)) {
 		CUDA_CHECK(cudaFuncSetAttribute(
 					ntt_cols_kernel<INV, K, CL, NP, APX, false>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1313,7 +1349,7 @@ static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
 	const size_t smem = (sizeof(ulonglong2) << K)
 		+ sizeof(u64) * (size_t) (xpad(1 << K) + 4);
 	if (p.tab) {
-		if (smem > 48 * 1024) {
+		if (smem_needs_optin(smem)) {
 			CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, true>,
 						cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		}
@@ -1321,7 +1357,7 @@ static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
 				threads, smem, p);
 		return;
 	}
-	if (smem > 48 * 1024) {
+	if (smem_needs_optin(smem)) {
 		CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, false>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}
@@ -1477,7 +1513,7 @@ static void run_rows_polymul(struct vkhel_ctx *ctx, fast_pass p) {
 	VK_REQUIRE(blocks <= 0x7fffffffull, "product too large for one launch");
 	const size_t smem = 2 * ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
 		+ (size_t) C::groups_per_cta * C::xbuf * sizeof(u64);
-	if (smem > 48 * 1024) {
+	if (smem_needs_optin(smem)) {
 		CUDA_CHECK(cudaFuncSetAttribute(ntt_rows_polymul_kernel<K, APX>,
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	}

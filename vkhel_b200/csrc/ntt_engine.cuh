@@ -87,19 +87,49 @@ struct tile_geom {
 	}
 };
 
+/* How the inverse transform's n^-1 factor is applied (inverse only; the pass
+ * that holds global stage 0, i.e. local stage 0 of a tile rooted at node 1):
+ *   FOLD_NONE   not in this pass
+ *   FOLD_LAST   in the last stage: both outputs of every butterfly of stage 0
+ *               are multiplied (n^-1 and inv_root[1] * n^-1) -- n/2 extra
+ *               products per transform
+ *   FOLD_TWID   in the twiddles.  A Gentleman-Sande butterfly multiplies only
+ *               its difference, so a coefficient is "unscaled" as long as it
+ *               has been on the sum side of every stage of this pass so far,
+ *               i.e. while the index bits paired so far are all zero.  A
+ *               butterfly whose inputs are unscaled takes its twiddle from the
+ *               table of inv_root * n^-1 (`tws`): its difference leaves scaled,
+ *               its sum stays unscaled.  Both inputs of a butterfly always have
+ *               the same history, and scaled inputs use the plain twiddle.
+ *               After the last stage exactly one coefficient of the tile
+ *               (index 0) is still unscaled and gets the one explicit product.
+ *               Which butterflies are concerned is static per register (the
+ *               pair bits of this round below the current one are zero) and per
+ *               thread (the bits paired in earlier rounds are zero), so the
+ *               only run-time cost is one pointer select per round. */
+enum { FOLD_NONE = 0, FOLD_LAST = 1, FOLD_TWID = 2 };
+
 /* One round of butterflies on NP interleaved tiles x[p][0..7] that share their
  * twiddles (NP batch entries of the same limb and tile position, or NP adjacent
  * columns): every (w, w') pair fetched from shared memory feeds NP butterflies.
  *   twt: the tile's twiddle subtree in shared memory, twt[node] = (w, w')
- *   FOLD: inverse only -- local stage 0 is global stage 0: multiply by n^-1
- *         (fold_a = n^-1, fold_b = inv_root[1] * n^-1) instead of node 1.
+ *   tws: FOLD_TWID only -- the same subtree of the scaled inverse table
+ *   FOLD: see above; fold_a = n^-1, fold_b = inv_root[1] * n^-1
  *   APX:  butterflies around the approximate Shoup product (bq = 3q) */
-template <int K, bool INV, bool FOLD, int NP, bool APX>
+template <int K, bool INV, int FOLD, int NP, bool APX>
 __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 		const ulonglong2 *twt, u64 q, u64 bq, ulonglong2 fold_a,
-		ulonglong2 fold_b) {
+		ulonglong2 fold_b, const ulonglong2 *tws = nullptr) {
 	using G = tile_geom<K>;
+	static_assert(INV || FOLD == FOLD_NONE, "only the inverse carries n^-1");
 	const int cnt = G::cnt(r);
+	/* FOLD_TWID: the index bits paired in earlier rounds are the low
+	 * K - 3(r+1) bits of the tile index, all taken from t (none for the round
+	 * the inverse starts with) */
+	const int hist_bits = G::full(r) ? K - 3 * (r + 1) : 0;
+	const bool unscaled_thread = FOLD == FOLD_TWID
+		&& (t & ((1 << hist_bits) - 1)) == 0;
+	const ulonglong2 *twu = FOLD == FOLD_TWID && unscaled_thread ? tws : twt;
 #pragma unroll
 	for (int step = 0; step < 3; step++) {
 		if (step >= cnt) {
@@ -109,12 +139,15 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 		const int u = 3 * r + j;                    /* local stage */
 		const int beta = cnt - 1 - j;               /* pair bit inside e */
 		const ulonglong2 *twp = twt + (1 << u) + G::gbase(r, j, t);
+		const ulonglong2 *twpu = twu + (1 << u) + G::gbase(r, j, t);
 #pragma unroll
 		for (int e = 0; e < 8; e++) {
 			if (e & (1 << beta)) {
 				continue;
 			}
-			if (INV && FOLD && u == 0) {
+			/* inputs that have only seen sums inside this round so far */
+			const bool upos = FOLD == FOLD_TWID && (e & ((1 << beta) - 1)) == 0;
+			if (INV && FOLD == FOLD_LAST && u == 0) {
 #pragma unroll
 				for (int p = 0; p < NP; p++) {
 					u64 &X = x[p][e];
@@ -128,7 +161,8 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 					Y = shoup_lazy(d, fold_b.x, fold_b.y, q);
 				}
 			} else {
-				const ulonglong2 w = twp[G::goff(r, j, e)];
+				const ulonglong2 w = upos ? twpu[G::goff(r, j, e)]
+					: twp[G::goff(r, j, e)];
 #pragma unroll
 				for (int p = 0; p < NP; p++) {
 					u64 &X = x[p][e];
@@ -141,22 +175,32 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 						else ct_lazy(X, Y, w.x, w.y, q, bq);
 					}
 				}
+				if (INV && FOLD == FOLD_TWID && u == 0 && upos) {
+					/* the tile's coefficient 0 (register 0 of group-thread 0):
+					 * the one value no difference has scaled */
+					if (unscaled_thread) {
+#pragma unroll
+						for (int p = 0; p < NP; p++) {
+							x[p][e] = shoup_lazy(x[p][e], fold_a.x, fold_a.y, q);
+						}
+					}
+				}
 			}
 		}
 	}
 }
 
 /* canonical residue of a value at the end of a transform: forward values are
- * below 2*bq, inverse values below bq (bq = 2q exact, 3q approximate) */
-template <bool INV, bool APX>
+ * below 2*bq, inverse values below bq (bq = 2q exact, 3q approximate); the
+ * FOLD_LAST stage leaves [0,2q) in both families */
+template <bool INV, bool APX, int FOLD = FOLD_LAST>
 __device__ __forceinline__ u64 tile_canon(u64 v, u64 q, u64 bq) {
 	if (!INV) {
 		v = csub(v, bq);        /* [0,2bq) -> [0,bq) */
-		if (APX) {
-			v = csub(v, q);     /* [0,3q) -> [0,2q) */
-		}
 	}
-	/* inverse: the folded last stage leaves [0,2q) in both families */
+	if (APX && (!INV || FOLD == FOLD_TWID)) {
+		v = csub(v, q);         /* [0,3q) -> [0,2q) */
+	}
 	return csub(v, q);
 }
 

@@ -116,7 +116,7 @@ extern "C" struct vkhel_ntt_tables *vkhel_ntt_tables_create_on(
 	TB_MARK("powers");
 	const size_t pair_bytes = 2 * n * sizeof(ulonglong2);
 	char *dev_buf = (char *) ntt_tables_mirror_alloc(ctx,
-			sizeof(limb_desc) + pair_bytes);
+			sizeof(limb_desc) + mirror_pair_bytes(n));
 	TB_MARK("mirror alloc");
 	ulonglong2 *pairs = (ulonglong2 *) (dev_buf + sizeof(limb_desc));
 	u64 *planar = (u64 *) device_alloc(ctx, pair_bytes);
