@@ -81,12 +81,18 @@ class c_stdout_to_stderr:
 
 # ---- clocks --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """nvidia-smi clocks / throttle reasons during the timed region.
+
+    One long-lived `nvidia-smi -lms` process, started well before the timed
+    region (its start-up takes a few hundred milliseconds on a fresh box);
+    every line is stamped on arrival and stop(t0, t1) keeps the samples that
+    fall inside the timed region [t0, t1]."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,"
              "clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 20
 
     def __init__(self, device):
         self.device = device
@@ -98,7 +104,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device),
                  "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -108,35 +114,59 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        """block (bounded) until nvidia-smi has delivered its first line"""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
                     "note": "nvidia-smi unavailable"}
-        time.sleep(0.15)
+        time.sleep(2.5 * self.PERIOD_MS / 1e3)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(lo, hi):
+            sm, smax, reasons, power = [], [], set(), []
+            for stamp, line in self.lines:
+                if stamp < lo or stamp > hi:
+                    continue
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    smax.append(float(parts[1]))
+                    power.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, reasons, power
+
+        # a line is stamped when it arrives, one sampling period at most after
+        # the reading it carries
+        slack = self.PERIOD_MS / 1e3
+        sm, smax, reasons, power = collect(t0, t1 + slack)
+        note = "samples inside the timed region"
+        if not sm:
+            # timed region shorter than the sampling period: the nearest
+            # samples around it (the GPU is under the same load: warm-up steps
+            # before, the forward-only / inverse-only timing after)
+            sm, smax, reasons, power = collect(t0 - 0.2, t1 + 0.2)
+            note = "timed region shorter than one sampling period: samples within 0.2 s of it"
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "period_ms": self.PERIOD_MS,
+                "reasons": sorted(reasons), "note": note}
 
 
 # ---- workload ------------------------------------------------------------------------
@@ -206,7 +236,15 @@ def run_reference_arm(args):
     psis = [params.find_psi(N, q) for q in primes[:4]]
     cores = os.cpu_count() or 1
     rate, cores, sample, dt, (tables, x) = cpu_arm(primes, psis, 2.0)
-    sample_polys = x.size // N
+    # one step = the per-GPU batch (512 polynomials) when K + W steps of it
+    # fit in about two minutes, else the largest sample that does
+    limbs = len(tables)
+    budget_polys = rate / 2 * 120.0 / (args.steps + max(args.warmup, 1))
+    sample_polys = int(min(x.size // N, max(budget_polys, cores, limbs)))
+    sample_polys = max(sample_polys - sample_polys % limbs, limbs)
+    x = x[:sample_polys * N]
+    sample = ("%d polys of n=2^16 over %d limbs, forward+inverse, OpenMP over "
+              "polynomials" % (sample_polys, limbs))
     for _ in range(max(args.warmup - 1, 0)):
         oracle.inverse_batch(oracle.forward_batch(x, tables, threads=cores),
                              tables, threads=cores)
@@ -332,35 +370,51 @@ def run_native_arm(args):
 
     timer = ctx.timer()
 
+    timed_window = [0.0, 0.0]   # host clock around the last timed region
+
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
             step_fn()
         ctx.sync()
         barrier()
         l0 = ctx.launch_count
+        timed_window[0] = time.perf_counter()
         timer.start()
         for _ in range(steps):
             step_fn()
         timer.stop()
         ms = timer.elapsed_ms()
         ctx.sync()
+        timed_window[1] = time.perf_counter()
         barrier()
         return max_over_ranks(ms), ctx.launch_count - l0
 
     # bring the GPU out of its idle clocks before anything is timed: an idle
     # B200 sits at 120 MHz and needs tens of milliseconds of load to reach its
     # boost clock; W steps of 0.8 ms are too short for that
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.25:
         for _ in range(20):
             step_resident()
         ctx.sync()
-
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        # keep the GPU under load while nvidia-smi starts up
+        while (sampler.proc and not sampler.lines
+               and time.perf_counter() - t_spin < 5.0):
+            for _ in range(20):
+                step_resident()
+            ctx.sync()
+    barrier()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    window = tuple(timed_window)
+    # the same load continues while the last samples arrive
+    for _ in range(60):
+        step_resident()
+    ctx.sync()
+    clocks = sampler.stop(*window) if rank == 0 else None
 
     # correctness of what was just timed: the round trip returns the input
     work.download(host_out)
@@ -511,7 +565,7 @@ def run_native_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true",

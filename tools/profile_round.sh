@@ -25,6 +25,12 @@ python tools/ncu_summary.py $out/prof_$tag.ncu-rep > $out/ncu_full_$tag.txt 2>&1
 python tools/ncu_summary.py $out/prof_polymul_$tag.ncu-rep > $out/ncu_full_polymul_$tag.txt 2>&1
 rm -f $out/prof_polymul_$tag.ncu-rep
 python tools/sweep.py > $out/sweep_$tag.jsonl 2>/dev/null
+python tools/elem_bench.py 2>/dev/null | tail -1 > $out/elem_$tag.json
+# one element-wise kernel, full metric set (HBM-bound: DRAM throughput)
+ncu --set full --clock-control none -k regex:elem_vec -s 6 -c 2 \
+    -f -o $out/prof_elem_$tag python tools/elem_bench.py > /dev/null 2>&1
+python tools/ncu_summary.py $out/prof_elem_$tag.ncu-rep > $out/ncu_full_elem_$tag.txt 2>&1
+rm -f $out/prof_elem_$tag.ncu-rep
 python tools/pcie_probe.py 2>/dev/null | tail -1 > $out/pcie_$tag.json
 python tools/tables_bench.py 2>/dev/null | grep config > $out/tables_$tag.jsonl
 for a in "10 4096" "12 1024" "14 256" "16 64"; do
