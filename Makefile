@@ -87,7 +87,7 @@ $(BIN_DIR)/api_loop: examples/api_loop.c $(STATIC)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 
 # micro-benchmarks behind the roofline denominators (profiles/*bench*.txt)
-tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench
+tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench $(BIN_DIR)/exchange_bench
 $(BIN_DIR)/%_bench: tools/%_bench.cu
 	@mkdir -p $(BIN_DIR)
 	$(NVCC) $(ARCH) -O3 -o $@ $<

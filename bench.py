@@ -508,7 +508,8 @@ def run_native_arm(args):
                         "+ copy out + vkhel_vector_unmap (which writes the "
                         "vector back, as the reference does); host wall "
                         "clock"},
-            "gpu_launches": launches,
+            # whole job: every rank launches the same kernels on its shard
+            "gpu_launches": launches * world,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,

@@ -38,4 +38,5 @@ for a in "10 4096" "12 1024" "14 256" "16 64"; do
 done > $out/api_loop_$tag.jsonl
 build/bin/bfly_bench > $out/bfly_bench_$tag.txt 2>&1
 build/bin/pipe_bench > $out/pipe_bench_$tag.txt 2>&1
+build/bin/exchange_bench > $out/exchange_bench_$tag.txt 2>&1
 ls -la $out | tail -20
