@@ -44,7 +44,7 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 
 .PHONY: all libs oracle refbins examples tools clean check check-host
 all: libs oracle refbins examples
-examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop
+examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop $(BIN_DIR)/api_product
 libs: $(SHARED) $(STATIC)
 refbins: $(REF_BINS)
 
@@ -83,6 +83,11 @@ $(BIN_DIR)/multi_gpu: examples/multi_gpu.c $(STATIC)
 
 # the reference API in a loop over separate vectors (recorded transforms)
 $(BIN_DIR)/api_loop: examples/api_loop.c $(STATIC)
+	@mkdir -p $(BIN_DIR)
+	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# the reference's polynomial product sequence (recorded transforms + fused product)
+$(BIN_DIR)/api_product: examples/api_product.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 

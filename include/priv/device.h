@@ -54,6 +54,7 @@ struct device_ctx {
 	void *defer;         /* recorded single-vector transforms (opaque, C++) */
 	uint64_t deferred_batches;    /* indirect batches launched so far */
 	uint64_t deferred_transforms; /* transforms that went out in them */
+	uint64_t fused_products;      /* elemmul calls fused into the inverse that followed */
 };
 
 void device_ctx_init(struct device_ctx *dev, int device);

@@ -114,6 +114,12 @@ uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *);
 void vkhel_ctx_deferred_stats(const struct vkhel_ctx *, uint64_t *batches,
 		uint64_t *transforms);
 void vkhel_ctx_flush(struct vkhel_ctx *);
+/* vkhel_vector_elemmul (reference src/vector.c:388-427) is recorded as well:
+ * when the next call is the in-place vkhel_vector_inverse_transform of its
+ * result with the same modulus -- the reference's polynomial product -- the
+ * multiplication happens inside the inverse transform's first pass; any other
+ * call launches the product first.  Number of products fused so far: */
+uint64_t vkhel_ctx_fused_products(const struct vkhel_ctx *);
 /* write a buffer larger than L2 so the next kernel starts cold */
 void vkhel_ctx_flush_l2(struct vkhel_ctx *);
 

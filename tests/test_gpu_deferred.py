@@ -222,3 +222,158 @@ def test_inverse_with_tail_and_unsupported_moduli_bypass_the_queue(ctx):
     ctx.forward_transform(w, w, ts.lib)          # strict path, 63-bit modulus
     assert np.array_equal(w.to_host(), oracle.forward(y, ts.ora))
     v.destroy(), w.destroy(), t.destroy(), ts.destroy()
+
+
+# ---- recorded product: elemmul fused into the in-place inverse that follows --------------
+def product_oracle(a, b, t):
+    return oracle.inverse(oracle.elemmul(a, b, t.q), t.ora)
+
+
+@pytest.mark.parametrize("log2n", [3, 5, 8, 9, 11, 12, 14, 16])
+@pytest.mark.parametrize("q", [params.P0, params.Q61, params.Q62_LAZY_MAX])
+def test_reference_polymul_sequence_is_fused(ctx, log2n, q):
+    """forward, forward, elemmul, inverse in place -- the reference's product
+    (examples/example.c:18-60): same result as the separate launches, and the
+    product went out inside the inverse transform"""
+    n = 1 << log2n
+    if (q - 1) % (2 * n):
+        pytest.skip("modulus without a 2n-th root of unity")
+    t = Tables(n, q)
+    rng = np.random.default_rng(log2n)
+    x, y = rand_mod(rng, n, q), rand_mod(rng, n, q)
+    a, b = ctx.from_host(x), ctx.from_host(y)
+    c = ctx.vector(n)
+    f0 = ctx.fused_products
+    ctx.forward_transform(a, a, t.lib)
+    ctx.forward_transform(b, b, t.lib)
+    ctx.elemmul(a, b, c, q)
+    ctx.inverse_transform(c, c, t.lib)
+    fx, fy = oracle.forward(x, t.ora), oracle.forward(y, t.ora)
+    assert np.array_equal(c.to_host(), product_oracle(fx, fy, t))
+    assert np.array_equal(a.to_host(), fx)      # the factors are untouched
+    assert np.array_equal(b.to_host(), fy)
+    assert ctx.fused_products == f0 + 1
+    for v in (a, b, c):
+        v.destroy()
+    t.destroy()
+
+
+@pytest.mark.parametrize("alias", ["a", "b", "both"])
+def test_fused_product_in_place(ctx, alias):
+    n = 1 << 12
+    t = Tables(n, params.P0)
+    rng = np.random.default_rng(7)
+    x, y = rand_mod(rng, n, t.q), rand_mod(rng, n, t.q)
+    a, b = ctx.from_host(x), ctx.from_host(y)
+    f0 = ctx.fused_products
+    if alias == "a":
+        ctx.elemmul(a, b, a, t.q)
+        ctx.inverse_transform(a, a, t.lib)
+        got, want = a.to_host(), product_oracle(x, y, t)
+        assert np.array_equal(b.to_host(), y)
+    elif alias == "b":
+        ctx.elemmul(a, b, b, t.q)
+        ctx.inverse_transform(b, b, t.lib)
+        got, want = b.to_host(), product_oracle(x, y, t)
+        assert np.array_equal(a.to_host(), x)
+    else:
+        ctx.elemmul(a, a, a, t.q)
+        ctx.inverse_transform(a, a, t.lib)
+        got, want = a.to_host(), product_oracle(x, x, t)
+    assert np.array_equal(got, want)
+    assert ctx.fused_products == f0 + 1
+    a.destroy()
+    b.destroy()
+    t.destroy()
+
+
+def test_fused_product_of_arbitrary_64_bit_factors(ctx):
+    """elemmul reduces both factors (reference elemmul.comp:62-73); the fused
+    kernel must do the same for operands that are not canonical residues"""
+    n = 1 << 10
+    t = Tables(n, params.P0)
+    rng = np.random.default_rng(11)
+    x = rng.integers(0, 1 << 64, n, dtype=np.uint64)
+    y = rng.integers(0, 1 << 64, n, dtype=np.uint64)
+    x[:3] = np.array([2**64 - 1, t.q, t.q - 1], dtype=np.uint64)
+    y[:3] = np.array([2**64 - 1, 2**64 - 1, t.q + 1], dtype=np.uint64)
+    a, b = ctx.from_host(x), ctx.from_host(y)
+    c = ctx.vector(n)
+    f0 = ctx.fused_products
+    ctx.elemmul(a, b, c, t.q)
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), product_oracle(x, y, t))
+    assert ctx.fused_products == f0 + 1
+    for v in (a, b, c):
+        v.destroy()
+    t.destroy()
+
+
+def test_recorded_product_is_launched_when_anything_else_follows(ctx):
+    n = 1 << 11
+    t = Tables(n, params.P0)
+    t2 = Tables(n, params.Q61)
+    rng = np.random.default_rng(13)
+    x, y = rand_mod(rng, n, t.q), rand_mod(rng, n, t.q)
+    prod = oracle.elemmul(x, y, t.q)
+    a, b = ctx.from_host(x), ctx.from_host(y)
+    f0 = ctx.fused_products
+
+    # read back right away
+    c = ctx.vector(n)
+    ctx.elemmul(a, b, c, t.q)
+    assert np.array_equal(c.to_host(), prod)
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), oracle.inverse(prod, t.ora))
+
+    # inverse out of place: the product stays visible
+    d = ctx.vector(n)
+    ctx.elemmul(a, b, c, t.q)
+    ctx.inverse_transform(c, d, t.lib)
+    assert np.array_equal(d.to_host(), oracle.inverse(prod, t.ora))
+    assert np.array_equal(c.to_host(), prod)
+
+    # another modulus' tables
+    ctx.elemmul(a, b, c, t.q)
+    ctx.inverse_transform(c, c, t2.lib)
+    assert np.array_equal(c.to_host(), oracle.inverse(prod, t2.ora))
+
+    # a second product on top of the first, a forward transform, elemfma, dup
+    ctx.elemmul(a, b, c, t.q)
+    ctx.elemmul(c, b, d, t.q)
+    ctx.forward_transform(d, d, t.lib)
+    assert np.array_equal(c.to_host(), prod)
+    assert np.array_equal(
+        d.to_host(), oracle.forward(oracle.elemmul(prod, y, t.q), t.ora))
+    ctx.elemmul(a, b, c, t.q)
+    ctx.elemfma(c, b, d, 3, t.q)
+    assert np.array_equal(d.to_host(), oracle.elemfma(prod, y, 3, t.q))
+    ctx.elemmul(a, b, c, t.q)
+    e = c.dup()
+    assert np.array_equal(e.to_host(), prod)
+
+    # an operand is overwritten / destroyed before the inverse
+    ctx.elemmul(a, b, c, t.q)
+    a.copy_from_host(y)
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), oracle.inverse(prod, t.ora))
+    ctx.elemmul(a, b, c, t.q)           # a == y now
+    b.destroy()
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(),
+                          oracle.inverse(oracle.elemmul(y, y, t.q), t.ora))
+    assert ctx.fused_products == f0
+
+    # result longer than the transform: the tail is scaled, nothing is fused
+    big = ctx.from_host(np.concatenate([x, x]))
+    big2 = ctx.from_host(np.concatenate([y, y]))
+    ctx.elemmul(big, big2, big, t.q)
+    ctx.inverse_transform(big, big, t.lib)
+    want = oracle.inverse(prod, t.ora, out_len=2 * n,
+                          out_init=np.concatenate([prod, prod]))
+    assert np.array_equal(big.to_host(), want)
+    assert ctx.fused_products == f0
+    for v in (a, c, d, e, big, big2):
+        v.destroy()
+    t.destroy()
+    t2.destroy()

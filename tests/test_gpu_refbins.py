@@ -45,3 +45,21 @@ def test_multi_gpu_example():
                              timeout=300)
         assert res.returncode == 0, res.stdout + res.stderr
         assert "== single-GPU result" in res.stdout
+
+
+@pytest.mark.parametrize("env", [{}, {"VKHEL_NO_FUSED_PRODUCT": "1"},
+                                 {"VKHEL_NO_DEFER": "1"}])
+def test_api_product_example(env):
+    """examples/api_product.c: the reference's product sequence (forward,
+    forward, elemmul, inverse in place) from C against the schoolbook product;
+    by default the element-wise product goes out inside the inverse"""
+    path = os.path.join(BIN, "api_product")
+    if not os.path.exists(path):
+        pytest.fail("%s missing: run `make`" % path)
+    for args in (["3", "5"], ["8", "9"], ["10", "7"], ["12", "6"], ["16", "2"]):
+        res = subprocess.run([path] + args, capture_output=True, text=True,
+                             timeout=300, env=dict(os.environ, **env))
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert '"matches_schoolbook": true' in res.stdout
+        fused = '"fused_products": 0,' not in res.stdout
+        assert fused == (not env), res.stdout

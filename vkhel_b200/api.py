@@ -82,6 +82,7 @@ SIGNATURES = {
     "vkhel_ctx_flush": (None, [_vp]),
     "vkhel_ntt_tables_create_on": (_vp, [_vp, _u64, _u64, _u64]),
     "vkhel_ctx_deferred_stats": (None, [_vp, _p64, _p64]),
+    "vkhel_ctx_fused_products": (ctypes.c_uint64, [_vp]),
 }
 
 _lib = None
@@ -253,6 +254,11 @@ class Context:
         lib().vkhel_ctx_deferred_stats(self.handle, ctypes.byref(b),
                                        ctypes.byref(t))
         return int(b.value), int(t.value)
+
+    @property
+    def fused_products(self):
+        """elemmul calls that were fused into the inverse transform after them"""
+        return int(lib().vkhel_ctx_fused_products(self.handle))
 
     @property
     def launch_count(self):

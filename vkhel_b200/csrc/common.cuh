@@ -106,8 +106,10 @@ void launch_elemmodbytwo(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, uint64_t q_max);
-/* inverse transform of the point-wise product src * src2 (both canonical, in
- * the transform domain); returns false when the fused kernel does not apply
+/* kernel launches of one transform launched by launch_ntt on the fast path */
+unsigned ntt_launches_per_transform(unsigned log2n);
+/* inverse transform of the point-wise product src * src2 (any 64-bit values,
+ * reduced like the reference's elemmul); returns false when the fused kernel does not apply
  * and the caller has to multiply separately */
 bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,

@@ -239,6 +239,10 @@ extern "C" void vkhel_ctx_deferred_stats(const struct vkhel_ctx *ctx,
 	}
 }
 
+extern "C" uint64_t vkhel_ctx_fused_products(const struct vkhel_ctx *ctx) {
+	return ctx->dev.fused_products;
+}
+
 extern "C" void vkhel_ctx_flush(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
 	defer_flush(ctx);

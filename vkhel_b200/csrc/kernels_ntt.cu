@@ -563,8 +563,7 @@ ntt_rows_kernel(const fast_pass p) {
 			}
 			if (MUL) {
 				/* fused point-wise product (the reference's elemmul between
-				 * the forward and the inverse transform, src/vector.c:388-427):
-				 * both factors are canonical transform outputs */
+				 * the forward and the inverse transform, src/vector.c:388-427) */
 				modulus m;
 				m.q = q;
 				m.d = d.mm_d;
@@ -575,7 +574,15 @@ ntt_rows_kernel(const fast_pass p) {
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					const u64 y = active[pp] ? sp2[G::eoff(first, e)] : 0;
-					x[pp][e] = mulmod(x[pp][e], y, m);
+					/* (x mod q)(y mod q) mod q for ANY 64-bit factors, like
+					 * the reference's elemmul (elemmul.comp:62-73): the high
+					 * word is reduced first when it is not already below q --
+					 * a branch canonical factors never take */
+					u64 hi = __umul64hi(x[pp][e], y);
+					if (hi >= q) {
+						hi = reduce128(0, hi, m);
+					}
+					x[pp][e] = reduce128(hi, x[pp][e] * y, m);
 				}
 			}
 		}
@@ -864,9 +871,10 @@ ntt_rows_polymul_kernel(const fast_pass p) {
 #define SINGLE_MAX_LOG2N 11
 #endif
 
-template <bool INV, int K, bool APX, bool IND>
+template <bool INV, int K, bool APX, bool IND, bool MUL = false>
 __global__ void __launch_bounds__(1 << (K - 3), (1024 >> (K - 3)) > 16 ? 16 : (1024 >> (K - 3)))
 ntt_single_kernel(const fast_pass p) {
+	static_assert(!MUL || (INV && !IND), "fused product: direct inverse only");
 	using G = tile_geom<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	ulonglong2 *sm_tw = (ulonglong2 *) smem_raw;           /* [2^K] */
@@ -928,6 +936,26 @@ ntt_single_kernel(const fast_pass p) {
 #pragma unroll
 			for (int e = 0; e < 8; e++) {
 				x[0][e] = sp[tb_first + G::eoff(first, e)];
+			}
+		}
+		if (MUL) {
+			/* fused point-wise product, as in the row pass: (x mod q)(y mod q)
+			 * mod q for any 64-bit factors */
+			modulus m;
+			m.q = q;
+			m.d = d.mm_d;
+			m.v = d.mm_v;
+			m.s = d.mm_s;
+			m.mu = 0;
+			const u64 *sp2 = p.src2 + (poly << K) + tb_first;
+#pragma unroll
+			for (int e = 0; e < 8; e++) {
+				const u64 y = sp2[G::eoff(first, e)];
+				u64 hi = __umul64hi(x[0][e], y);
+				if (hi >= q) {
+					hi = reduce128(0, hi, m);
+				}
+				x[0][e] = reduce128(hi, x[0][e] * y, m);
 			}
 		}
 		if (!tw_ready) {
@@ -1348,6 +1376,19 @@ static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = (sizeof(ulonglong2) << K)
 		+ sizeof(u64) * (size_t) (xpad(1 << K) + 4);
+	if constexpr (INV) {
+		if (p.src2) {
+			if (smem_needs_optin(smem)) {
+				CUDA_CHECK(cudaFuncSetAttribute(
+							ntt_single_kernel<true, K, APX, false, true>,
+							cudaFuncAttributeMaxDynamicSharedMemorySize,
+							(int) smem));
+			}
+			launch_fast(ctx, ntt_single_kernel<true, K, APX, false, true>,
+					(unsigned) blocks, threads, smem, p);
+			return;
+		}
+	}
 	if (p.tab) {
 		if (smem_needs_optin(smem)) {
 			CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, true>,
@@ -1390,6 +1431,14 @@ static unsigned single_max_log2n() {
 	return (unsigned) v;
 }
 
+/* kernel launches of one directly launched fast-path transform */
+unsigned ntt_launches_per_transform(unsigned log2n) {
+	if (log2n <= 8 || log2n <= single_max_log2n()) {
+		return 1;
+	}
+	return log2n <= 18 ? 2 : 3;
+}
+
 /* stage split of the fast path: [lead (generic, strided)] [col] [row] */
 struct fast_plan {
 	unsigned lead, kcol, krow;
@@ -1430,8 +1479,9 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	p.hgroup_log2 = 0;
 	p.bchunk = 1;
 
-	if (!src2 && log2n >= 9 && log2n <= single_max_log2n()) {
+	if ((!src2 || INV) && log2n >= 9 && log2n <= single_max_log2n()) {
 		p.src = src;
+		p.src2 = INV ? src2 : NULL;
 		p.dst = dst;
 		p.s0 = 0;
 		run_single_k<INV, APX>(ctx, p, log2n);

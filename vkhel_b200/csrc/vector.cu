@@ -57,7 +57,16 @@ struct defer_item {
 	unsigned table;     /* index into defer_queue::tables */
 };
 
+/* A recorded vkhel_vector_elemmul, see "recorded product" below */
+struct pending_product {
+	bool active;
+	const struct vkhel_vector *a, *b;
+	struct vkhel_vector *result;
+	uint64_t mod;
+};
+
 struct defer_queue {
+	pending_product mul;
 	bool inverse;
 	uint64_t log2n;
 	std::vector<struct vkhel_ntt_tables *> tables;   /* distinct, <= DEFER_TABLES */
@@ -73,6 +82,7 @@ struct defer_queue {
 static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 	if (!ctx->dev.defer) {
 		defer_queue *dq = new defer_queue();
+		dq->mul.active = false;
 		dq->inverse = false;
 		dq->log2n = 0;
 		dq->half = 0;
@@ -118,19 +128,35 @@ static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 	}
 }
 
+static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq);
+
 void defer_flush(struct vkhel_ctx *ctx) {
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
-	if (!dq || dq->items.empty()) {
+	if (!dq) {
+		return;
+	}
+	if (dq->items.empty()) {
+		/* transforms and a product are never recorded at the same time: each
+		 * launches the other kind when it is recorded */
+		flush_product(ctx, dq);
 		return;
 	}
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
 	const size_t count = dq->items.size();
 	const size_t ntab = dq->tables.size();
-	if (count == 1) {
-		struct vkhel_ntt_tables *ntt = dq->tables[0];
-		launch_ntt(ctx, dq->inverse, dq->items[0].ptrs.src,
-				dq->items[0].ptrs.dst, ntt_tables_device_desc(ctx, ntt), 1, 1,
-				(unsigned) ntt->log2n, ntt->q);
+	/* An indirect batch costs a pointer-table copy on top of its launches;
+	 * a record that short is cheaper launched transform by transform:
+	 * always a single one, and two where a transform is one launch (the
+	 * two forward transforms of the reference's product at n <= 2^11:
+	 * measured 12.3 us per product this way against 16.1 us batched). */
+	if (count == 1 || (count == 2
+				&& ntt_launches_per_transform((unsigned) dq->log2n) == 1)) {
+		for (const defer_item &it : dq->items) {
+			struct vkhel_ntt_tables *ntt = dq->tables[it.table];
+			launch_ntt(ctx, dq->inverse, it.ptrs.src, it.ptrs.dst,
+					ntt_tables_device_desc(ctx, ntt), 1, 1,
+					(unsigned) ntt->log2n, ntt->q);
+		}
 	} else {
 		/* the recorded transforms are independent of each other, so they
 		 * may be regrouped: by tables (an RNS polynomial held as one vector
@@ -222,6 +248,7 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 		return false;
 	}
 	defer_queue *dq = defer_get(ctx);
+	flush_product(ctx, dq);
 	const void *rd = operand->device.ptr, *wr = result->device.ptr;
 	unsigned table = 0;
 	if (!dq->items.empty()) {
@@ -259,6 +286,59 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 static inline u64 *dev_u64(const struct vkhel_vector *v) {
 	defer_flush(v->ctx);
 	return dev_u64_nodefer(v);
+}
+
+/* ---- recorded product ---------------------------------------------------------------
+ * The reference's polynomial product is the call sequence forward, forward,
+ * elemmul, inverse (src/vector.c:388-427,513-657; examples/example.c:18-60).
+ * When the inverse transform runs in place on the product, the product itself
+ * is never observable, and the row pass of the inverse can multiply while it
+ * loads (ntt_rows_kernel<.., MUL, ..>): one launch and one sweep over the
+ * vector less.  vkhel_vector_elemmul therefore only records (a, b, result,
+ * mod); the very next use of the context decides:
+ *   - vkhel_vector_inverse_transform(result, result, tables) with the same
+ *     modulus and n == result->length: one fused launch sequence;
+ *   - anything else (every other entry point passes through defer_flush or
+ *     defer_transform): the product is launched first, as if it had never
+ *     been held back.
+ * $VKHEL_NO_DEFER=1 turns this off together with the recorded transforms,
+ * $VKHEL_NO_FUSED_PRODUCT=1 only this. */
+static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq) {
+	if (!dq->mul.active) {
+		return;
+	}
+	dq->mul.active = false;
+	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+	const pending_product &m = dq->mul;
+	launch_elemmul(ctx, dev_u64_nodefer(m.a), dev_u64_nodefer(m.b),
+			dev_u64_nodefer(m.result), m.result->length, m.mod);
+}
+
+/* the inverse transform that follows a recorded product: true when the fused
+ * kernels have been launched */
+static bool fuse_product_into_inverse(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, struct vkhel_ntt_tables *ntt) {
+	struct vkhel_ctx *ctx = result->ctx;
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	if (!dq || !dq->mul.active) {
+		return false;
+	}
+	const pending_product m = dq->mul;
+	if (operand != result || result != m.result || m.mod != ntt->q
+			|| result->length != ntt->n || !dq->items.empty()) {
+		return false;   /* the caller's path launches the product first */
+	}
+	dq->mul.active = false;
+	if (launch_ntt_inverse_of_product(ctx, dev_u64_nodefer(m.a),
+				dev_u64_nodefer(m.b), dev_u64_nodefer(result),
+				ntt_tables_device_desc(ctx, ntt), 1, 1, (unsigned) ntt->log2n,
+				ntt->q)) {
+		ctx->dev.fused_products++;
+		return true;
+	}
+	/* no fused kernel for this size or modulus */
+	dq->mul.active = true;
+	return false;
 }
 
 /* An event on the compute stream that covers every operation up to serial
@@ -555,6 +635,22 @@ extern "C" void vkhel_vector_elemmul(
 	DBG("elemmul mod: %" PRIu64 "\n", mod);
 	DBG_VEC("a", a);
 	DBG_VEC("b", b);
+	static const bool off = getenv("VKHEL_NO_DEFER") != NULL
+		|| getenv("VKHEL_NO_FUSED_PRODUCT") != NULL;
+	/* candidates for the fused inverse-of-product: a power-of-two length the
+	 * fast transform path covers */
+	const uint64_t len = result->length;
+	if (!off && len >= 8 && (len & (len - 1)) == 0 && mod < (1ull << 62)) {
+		defer_flush(result->ctx);   /* what was recorded so far goes first */
+		defer_queue *dq = defer_get(result->ctx);
+		dq->mul.active = true;
+		dq->mul.a = a;
+		dq->mul.b = b;
+		dq->mul.result = result;
+		dq->mul.mod = mod;
+		DBG_VEC("result", result);
+		return;
+	}
 	launch_elemmul(result->ctx, dev_u64(a), dev_u64(b), dev_u64(result),
 			result->length, mod);
 	DBG_VEC("result", result);
@@ -681,6 +777,10 @@ extern "C" void vkhel_vector_inverse_transform(
 			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
 	DBG_VEC("operand", operand);
 	check_ntt("inverse_transform", operand, result, ntt, ntt->n);
+	if (fuse_product_into_inverse(operand, result, ntt)) {
+		DBG_VEC("result", result);
+		return;
+	}
 	if (ntt->n >= 2 && result->length == ntt->n
 			&& defer_transform(true, operand, result, ntt)) {
 		DBG_VEC("result", result);
