@@ -36,6 +36,11 @@ python tools/tables_bench.py 2>/dev/null | grep config > $out/tables_$tag.jsonl
 for a in "10 4096" "12 1024" "14 256" "16 64"; do
   build/bin/api_loop $a | tail -1; VKHEL_NO_DEFER=1 build/bin/api_loop $a | tail -1
 done > $out/api_loop_$tag.jsonl
+for a in "8 2048" "10 2048" "12 1024" "14 256" "16 64"; do
+  build/bin/api_product $a | tail -1
+  VKHEL_NO_FUSED_PRODUCT=1 build/bin/api_product $a | tail -1
+  VKHEL_NO_DEFER=1 build/bin/api_product $a | tail -1
+done > $out/api_product_$tag.jsonl
 build/bin/bfly_bench > $out/bfly_bench_$tag.txt 2>&1
 build/bin/pipe_bench > $out/pipe_bench_$tag.txt 2>&1
 build/bin/exchange_bench > $out/exchange_bench_$tag.txt 2>&1

@@ -124,12 +124,16 @@ bool launch_ntt_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		uint64_t polys, unsigned log2n, uint64_t q_max);
 
 /* the same transform on `polys` separate polynomials, polynomial i read from
- * tab[i].src, written to tab[i].dst (tab in device memory) and using
- * descs[i % limbs]; only where ntt_indirect_supported() */
+ * tab[i].src, written to tab[i].dst and using descs[i % limbs]; only where
+ * ntt_indirect_supported().  The pointer table is either `tab` in device
+ * memory or, for at most NTT_INLINE_PTRS polynomials, `host_tab` in host
+ * memory, which travels in the kernel parameters (exactly one is non-NULL). */
+#define NTT_INLINE_PTRS 8
 bool ntt_indirect_supported(unsigned log2n, uint64_t q);
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
 		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
-		uint64_t polys, unsigned log2n, uint64_t q_max);
+		uint64_t polys, unsigned log2n, uint64_t q_max,
+		const ntt_ptrs *host_tab = NULL);
 
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */

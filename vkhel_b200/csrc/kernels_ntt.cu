@@ -305,10 +305,26 @@ struct fast_pass {
 	 * pass of a transform reads what the first one wrote (tab[i].dst) */
 	const ntt_ptrs *tab;
 	unsigned tab_second;
+	/* a short indirect batch carries its pointers in the kernel parameters
+	 * (tab_inline of them, tab == NULL): no pointer-table copy to the device */
+	unsigned tab_inline;
+	ntt_ptrs inl[NTT_INLINE_PTRS];
 	/* limb slice: this launch covers limbs [limb0, limb0 + limbs) of vectors
 	 * laid out [batch][limbs_total][n]; descs already points at limb0.  The
 	 * whole vector: limb0 = 0, limbs_total = limbs. */
 	unsigned limbs_total, limb0;
+
+	__host__ __device__ bool indirect() const {
+		return tab != NULL || tab_inline != 0;
+	}
+	/* pointers of polynomial i of an indirect batch; p is a __grid_constant__
+	 * kernel parameter, so the inline table is read from constant memory */
+	__device__ __forceinline__ ntt_ptrs entry(u64 i) const {
+		if (tab_inline) {
+			return inl[i];
+		}
+		return tab[i];
+	}
 };
 
 /* padded position of tile element i in a warp-group's exchange buffer: 4 words
@@ -442,7 +458,7 @@ struct row_cfg {
 template <bool INV, int K, int NP, bool MUL, bool APX, bool IND>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
-ntt_rows_kernel(const fast_pass p) {
+ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 	static_assert(!(IND && MUL), "no indirect fused product");
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
@@ -535,7 +551,7 @@ ntt_rows_kernel(const fast_pass p) {
 				off[pp] = (u64) (H0 + h) << K;
 				ntt_ptrs ent = { NULL, NULL };
 				if (active[pp]) {
-					ent = p.tab[poly];
+					ent = p.entry(poly);
 				}
 				dbase[pp] = ent.dst;
 				sp = (p.tab_second ? ent.dst : ent.src) + off[pp] + tb_first;
@@ -740,7 +756,7 @@ __device__ __forceinline__ void rows_rounds(u64 (&x)[1][8], u64 *xb, int t,
 
 template <int K, bool APX>
 __global__ void __launch_bounds__(FAST_THREADS, PMUL_MIN_CTAS)
-ntt_rows_polymul_kernel(const fast_pass p) {
+ntt_rows_polymul_kernel(const __grid_constant__ fast_pass p) {
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -873,7 +889,7 @@ ntt_rows_polymul_kernel(const fast_pass p) {
 
 template <bool INV, int K, bool APX, bool IND, bool MUL = false>
 __global__ void __launch_bounds__(1 << (K - 3), (1024 >> (K - 3)) > 16 ? 16 : (1024 >> (K - 3)))
-ntt_single_kernel(const fast_pass p) {
+ntt_single_kernel(const __grid_constant__ fast_pass p) {
 	static_assert(!MUL || (INV && !IND), "fused product: direct inverse only");
 	using G = tile_geom<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -916,7 +932,7 @@ ntt_single_kernel(const fast_pass p) {
 		const u64 *sp;
 		u64 *dp;
 		if (IND) {
-			const ntt_ptrs ent = p.tab[poly];
+			const ntt_ptrs ent = p.entry(poly);
 			sp = ent.src;
 			dp = ent.dst;
 		} else {
@@ -1056,7 +1072,7 @@ __global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
 			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) > 0
 		? ((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
 			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) : 1)
-ntt_cols_kernel(const fast_pass p) {
+ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 	using G = tile_geom<K>;
 	using C = col_cfg<K, CL, NP>;
 	typedef typename col_vec<NP>::type vec_t;
@@ -1091,7 +1107,7 @@ ntt_cols_kernel(const fast_pass p) {
 	const u64 *src_base = p.src;
 	u64 *dst_base = p.dst;
 	if (IND) {
-		const ntt_ptrs ent = p.tab[poly];
+		const ntt_ptrs ent = p.entry(poly);
 		src_base = p.tab_second ? ent.dst : ent.src;
 		dst_base = ent.dst;
 	}
@@ -1228,7 +1244,7 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	const size_t smem = ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
 	if constexpr (!MUL) {
-		if (p.tab) {
+		if (p.indirect()) {
 			if (smem_needs_optin(smem)) {
 				CUDA_CHECK(cudaFuncSetAttribute(
 							ntt_rows_kernel<INV, K, NP, false, APX, true>,
@@ -1281,7 +1297,7 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL))
 		+ (INV && COLS_FOLD == FOLD_TWID && p.s0 == 0
 				? sizeof(ulonglong2) << K : 0);
-	if (p.tab) {
+	if (p.indirect()) {
 		if (smem_needs_optin(smem)) {
 			CUDA_CHECK(cudaFuncSetAttribute(
 						ntt_cols_kernel<INV, K, CL, NP, APX, true>,
@@ -1389,7 +1405,7 @@ static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
 			return;
 		}
 	}
-	if (p.tab) {
+	if (p.indirect()) {
 		if (smem_needs_optin(smem)) {
 			CUDA_CHECK(cudaFuncSetAttribute(ntt_single_kernel<INV, K, APX, true>,
 						cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1463,14 +1479,24 @@ template <bool INV, bool APX>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL,
-		unsigned limbs_total = 0, unsigned limb0 = 0) {
+		unsigned limbs_total = 0, unsigned limb0 = 0,
+		const ntt_ptrs *inline_tab = NULL) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
 	p.tab = tab;
 	p.tab_second = 0;
+	p.tab_inline = 0;
+	if (inline_tab) {
+		VK_REQUIRE(polys <= NTT_INLINE_PTRS, "internal: inline batch too long");
+		p.tab_inline = (unsigned) polys;
+		for (uint64_t i = 0; i < polys; i++) {
+			p.inl[i] = inline_tab[i];
+		}
+	}
 	p.limbs_total = limbs_total ? limbs_total : (unsigned) limbs;
 	p.limb0 = limb0;
-	VK_REQUIRE(!tab || !pl.lead, "internal: indirect batch of n > 2^18");
+	VK_REQUIRE(!p.indirect() || !pl.lead,
+			"internal: indirect batch of n > 2^18");
 	p.src2 = NULL;
 	p.descs = descs;
 	p.limbs = (unsigned) limbs;
@@ -1597,6 +1623,7 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	fast_pass p;
 	p.tab = NULL;
 	p.tab_second = 0;
+	p.tab_inline = 0;
 	p.limbs_total = (unsigned) limbs;
 	p.limb0 = 0;
 	p.src2 = NULL;
@@ -1832,14 +1859,17 @@ bool ntt_indirect_supported(unsigned log2n, uint64_t q) {
 
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
 		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
-		uint64_t polys, unsigned log2n, uint64_t q_max) {
+		uint64_t polys, unsigned log2n, uint64_t q_max,
+		const ntt_ptrs *host_tab) {
 	VK_REQUIRE(ntt_indirect_supported(log2n, q_max),
 			"internal: indirect batch outside the fast path");
+	VK_REQUIRE((tab != NULL) != (host_tab != NULL),
+			"internal: indirect batch needs exactly one pointer table");
 	if (use_approx(q_max, log2n)) {
-		if (inverse) run_fast<true, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
-		else run_fast<false, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
+		if (inverse) run_fast<true, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
+		else run_fast<false, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
 	} else {
-		if (inverse) run_fast<true, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
-		else run_fast<false, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab);
+		if (inverse) run_fast<true, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
+		else run_fast<false, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
 	}
 }

@@ -103,6 +103,14 @@ static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 		const std::vector<ntt_ptrs> &host, const limb_desc *descs,
 		uint64_t limbs, uint64_t q_max) {
 	const size_t count = host.size();
+	if (count <= NTT_INLINE_PTRS) {
+		/* short record: the pointers travel in the kernel parameters */
+		launch_ntt_indirect(ctx, dq->inverse, NULL, descs, limbs, count,
+				(unsigned) dq->log2n, q_max, host.data());
+		ctx->dev.deferred_batches++;
+		ctx->dev.deferred_transforms += count;
+		return;
+	}
 	size_t done = 0;
 	while (done < count) {
 		/* whole batch entries per piece of at most DEFER_MAX pointers */
