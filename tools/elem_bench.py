@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Element-wise kernels at 2^27 elements (HBM-bound): GB/s per operation.
-Knobs are read by the library: $VKHEL_ELEM_WAVES."""
+"""Element-wise kernels at 2^27 elements (HBM-bound): GB/s per operation
+(algorithmic bytes: 24 per element for the two-input kernels, 16 otherwise)."""
 import json
 import os
 import sys
@@ -23,8 +23,7 @@ def main():
     a = ctx.from_host(host)
     b = ctx.from_host(host[::-1].copy())
     c = ctx.vector(total, zero=False)
-    res = {"waves": os.environ.get("VKHEL_ELEM_WAVES", "default"),
-           "lib": os.path.basename(vk.LIB_PATH)}
+    res = {"lib": os.path.basename(vk.LIB_PATH), "elements": total}
     for name, fn, nbytes in (
             ("elemmul", lambda: ctx.elemmul(a, b, c, q), 24),
             ("elemfma", lambda: ctx.elemfma(a, b, c, 12345, q), 24),
