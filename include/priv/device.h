@@ -20,6 +20,11 @@ struct pinned_slot {
 	void *ptr;
 	size_t bytes;
 	int in_use;
+	/* released while a copy out of the buffer was still in flight: `event`
+	 * (cudaEvent_t, created on first use) marks the end of that copy and is
+	 * waited for before the buffer is handed out again */
+	int busy;
+	void *event;
 };
 
 struct device_ctx {

@@ -75,6 +75,8 @@ extern "C" void device_free(struct vkhel_ctx *ctx, void *ptr);
 extern "C" void *device_scratch(struct vkhel_ctx *ctx, size_t bytes);
 extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes);
 extern "C" void pinned_release(struct vkhel_ctx *ctx, void *ptr);
+extern "C" void pinned_release_after(struct vkhel_ctx *ctx, void *ptr,
+		void *stream);
 /* device pointer to the limb_desc of `ntt` on ctx's device (uploads the
  * mirror on first use) */
 const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,

@@ -166,6 +166,9 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	delete cache;
 
 	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
+		if (dev->pinned[i].event) {
+			CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->pinned[i].event));
+		}
 		if (dev->pinned[i].ptr) {
 			CUDA_CHECK(cudaFreeHost(dev->pinned[i].ptr));
 		}
@@ -295,34 +298,63 @@ extern "C" void *device_scratch(struct vkhel_ctx *ctx, size_t bytes) {
 	return dev->scratch;
 }
 
+/* the copy that was reading the slot's buffer when it was released is over */
+static void pinned_slot_settle(struct pinned_slot *slot) {
+	if (slot->busy) {
+		CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) slot->event));
+		slot->busy = 0;
+	}
+}
+
 extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes) {
 	ctx_enter(ctx);
 	struct device_ctx *dev = &ctx->dev;
 	if (bytes == 0) {
 		bytes = 8;
 	}
-	int free_slot = -1;
+	/* In order: a cached buffer that is large enough and idle; for small
+	 * requests a fresh buffer in an empty slot (so that consecutive staged
+	 * copies overlap instead of queueing on one buffer); a large-enough
+	 * buffer whose last copy is still in flight (waited for); a slot whose
+	 * too-small buffer is replaced; an uncached allocation. */
+	const size_t small = (size_t) 16 << 20;
+	int fit = -1, fit_busy = -1, empty = -1, victim = -1;
 	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
 		struct pinned_slot *slot = &dev->pinned[i];
 		if (slot->in_use) {
 			continue;
 		}
-		if (slot->ptr && slot->bytes >= bytes) {
-			slot->in_use = 1;
-			return slot->ptr;
-		}
-		if (free_slot < 0 || !slot->ptr) {
-			free_slot = i;
+		if (!slot->ptr) {
+			empty = empty < 0 ? i : empty;
+		} else if (slot->bytes >= bytes) {
+			if (!slot->busy) {
+				fit = fit < 0 ? i : fit;
+			} else {
+				fit_busy = fit_busy < 0 ? i : fit_busy;
+			}
+		} else {
+			victim = victim < 0 ? i : victim;
 		}
 	}
+	if (fit < 0 && fit_busy >= 0 && (bytes > small || empty < 0)) {
+		fit = fit_busy;
+	}
+	if (fit >= 0) {
+		struct pinned_slot *slot = &dev->pinned[fit];
+		pinned_slot_settle(slot);
+		slot->in_use = 1;
+		return slot->ptr;
+	}
 	void *ptr = NULL;
-	if (free_slot < 0) {
+	const int target = empty >= 0 ? empty : victim;
+	if (target < 0) {
 		/* more simultaneous maps than cache slots: uncached allocation */
 		CUDA_CHECK(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
 		return ptr;
 	}
-	struct pinned_slot *slot = &dev->pinned[free_slot];
+	struct pinned_slot *slot = &dev->pinned[target];
 	if (slot->ptr) {
+		pinned_slot_settle(slot);
 		CUDA_CHECK(cudaFreeHost(slot->ptr));
 	}
 	CUDA_CHECK(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
@@ -341,6 +373,33 @@ extern "C" void pinned_release(struct vkhel_ctx *ctx, void *ptr) {
 			return;
 		}
 	}
+	CUDA_CHECK(cudaFreeHost(ptr));
+}
+
+/* Release a staging buffer that a copy enqueued on `stream` is still reading:
+ * the caller does not wait; the buffer is not reused before that copy ends. */
+extern "C" void pinned_release_after(struct vkhel_ctx *ctx, void *ptr,
+		void *stream) {
+	ctx_enter(ctx);
+	struct device_ctx *dev = &ctx->dev;
+	for (int i = 0; i < VKHEL_PINNED_SLOTS; i++) {
+		struct pinned_slot *slot = &dev->pinned[i];
+		if (slot->ptr == ptr) {
+			if (!slot->event) {
+				cudaEvent_t ev;
+				CUDA_CHECK(cudaEventCreateWithFlags(&ev,
+							cudaEventDisableTiming));
+				slot->event = ev;
+			}
+			CUDA_CHECK(cudaEventRecord((cudaEvent_t) slot->event,
+						(cudaStream_t) stream));
+			slot->busy = 1;
+			slot->in_use = 0;
+			return;
+		}
+	}
+	/* uncached buffer: it is freed here, so the copy has to end first */
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) stream));
 	CUDA_CHECK(cudaFreeHost(ptr));
 }
 

@@ -455,19 +455,37 @@ extern "C" struct vkhel_vector *vkhel_vector_dup(struct vkhel_vector *src) {
 	return dup;
 }
 
+/* chunk of the staged host -> device copies below */
+#define STAGE_CHUNK_BYTES ((size_t) 8 << 20)
+
 extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 		const uint64_t *elements) {
 	/* The reference maps (a device->host copy it does not need), memcpys and
 	 * unmaps (vector.c:262-268).  Here: one host->device copy.  The source
 	 * may be pageable and may be reused by the caller as soon as this
-	 * returns, so the copy is completed before returning. */
+	 * returns, so it is copied into pinned staging buffers (chunks of 8 MiB
+	 * from the context's cache, each released when its transfer has ended)
+	 * and the transfers are left in flight: the call neither waits for them
+	 * nor for the kernels enqueued before it. */
 	if (!vec->length) {
 		return;
 	}
-	enter(vec->ctx);
-	CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec), elements, vec->device.bytes,
-				cudaMemcpyHostToDevice, ctx_stream(vec->ctx)));
-	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
+	struct vkhel_ctx *ctx = vec->ctx;
+	enter(ctx);
+	char *dst = (char *) dev_u64(vec);
+	const char *src = (const char *) elements;
+	size_t left = vec->device.bytes;
+	while (left) {
+		const size_t piece = left < STAGE_CHUNK_BYTES ? left : STAGE_CHUNK_BYTES;
+		void *stage = pinned_acquire(ctx, piece);
+		memcpy(stage, src, piece);
+		CUDA_CHECK(cudaMemcpyAsync(dst, stage, piece, cudaMemcpyHostToDevice,
+					ctx_stream(ctx)));
+		pinned_release_after(ctx, stage, ctx_stream(ctx));
+		dst += piece;
+		src += piece;
+		left -= piece;
+	}
 }
 
 extern "C" void vkhel_vector_map(struct vkhel_vector *vec, void **mem,
@@ -497,10 +515,10 @@ extern "C" void vkhel_vector_unmap(struct vkhel_vector *vec) {
 		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec), vec->host.ptr,
 					vec->device.bytes, cudaMemcpyHostToDevice,
 					ctx_stream(vec->ctx)));
-		/* the staging buffer goes back to the cache: finish the copy first */
-		CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
 	}
-	pinned_release(vec->ctx, vec->host.ptr);
+	/* the staging buffer goes back to the cache and is handed out again only
+	 * after this copy has ended; nothing waits here */
+	pinned_release_after(vec->ctx, vec->host.ptr, ctx_stream(vec->ctx));
 	vec->host.ptr = NULL;
 	vec->host.bytes = 0;
 }
