@@ -1467,12 +1467,42 @@ struct fast_plan {
 	unsigned lead, kcol, krow;
 };
 
+/* $VKHEL_KROW="12:6,15:6": stages of the row pass for given log2 n (tuning) */
+static unsigned krow_override(unsigned log2n) {
+	static int table[32];
+	static bool parsed = false;
+	if (!parsed) {
+		parsed = true;
+		const char *env = getenv("VKHEL_KROW");
+		while (env && *env) {
+			char *end;
+			const long l = strtol(env, &end, 10);
+			if (*end != ':') {
+				break;
+			}
+			const long k = strtol(end + 1, &end, 10);
+			if (l >= 9 && l <= 18 && k >= 3 && k <= 8 && l - k >= 3
+					&& l - k <= 10) {
+				table[l] = (int) k;
+			}
+			env = *end == ',' ? end + 1 : end;
+			if (*end != ',') {
+				break;
+			}
+		}
+	}
+	return log2n < 32 ? (unsigned) table[log2n] : 0;
+}
+
 static fast_plan plan_fast(unsigned log2n) {
 	fast_plan pl = { 0, 0, 0 };
 	if (log2n <= 8) {
 		pl.krow = log2n;
 	} else if (log2n <= 18) {
 		pl.krow = log2n - 8 >= 3 ? 8 : log2n - 3;
+		if (krow_override(log2n)) {
+			pl.krow = krow_override(log2n);
+		}
 		pl.kcol = log2n - pl.krow;
 	} else {
 		pl.krow = 8;
