@@ -1494,12 +1494,21 @@ static unsigned krow_override(unsigned log2n) {
 	return log2n < 32 ? (unsigned) table[log2n] : 0;
 }
 
-static fast_plan plan_fast(unsigned log2n) {
+/* `forward_only`: the plan of a plain forward transform, which may differ from
+ * the split the inverse and the fused product use */
+static fast_plan plan_fast(unsigned log2n, bool forward_only = false) {
 	fast_plan pl = { 0, 0, 0 };
 	if (log2n <= 8) {
 		pl.krow = log2n;
 	} else if (log2n <= 18) {
 		pl.krow = log2n - 8 >= 3 ? 8 : log2n - 3;
+		/* measured at 2^27 coefficients (tools/split_bench.py): forward
+		 * n = 2^13 as 6 + 7 1.067 ms against 1.094 as 5 + 8, n = 2^15 as 8 + 7
+		 * 1.156 against 1.207 as 7 + 8; the inverse gains nothing from
+		 * either, and every other size is best with the 8-stage row pass */
+		if (forward_only && (log2n == 13 || log2n == 15)) {
+			pl.krow = 7;
+		}
 		if (krow_override(log2n)) {
 			pl.krow = krow_override(log2n);
 		}
@@ -1518,7 +1527,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL,
 		unsigned limbs_total = 0, unsigned limb0 = 0,
 		const ntt_ptrs *inline_tab = NULL) {
-	const fast_plan pl = plan_fast(log2n);
+	const fast_plan pl = plan_fast(log2n, !INV);
 	fast_pass p;
 	p.tab = tab;
 	p.tab_second = 0;
