@@ -22,8 +22,10 @@
  * pass that contains the last stage stores canonical residues, which is what
  * the reference stores after every stage -- hence bit-identical output.  For
  * 2^62 <= q < 2^63 the strict butterflies keep every value canonical.  The
- * n^-1 scaling of the inverse is folded into its last stage (twiddles n^-1 and
- * inv_root[1] * n^-1).
+ * n^-1 scaling of the inverse costs no pass of its own: the column pass takes
+ * it from a scaled copy of the top of the inverse twiddle heap (FOLD_TWID,
+ * ntt_engine.cuh), the single-pass, row-only and generic kernels fold it into
+ * their last stage (twiddles n^-1 and inv_root[1] * n^-1, FOLD_LAST).
  */
 #include "common.cuh"
 #include "ntt_engine.cuh"
@@ -245,8 +247,9 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
  *                 every global and shared access is contiguous.
  *
  * Forward: column pass (stages 0..) then row pass; inverse: row pass then
- * column pass, whose last stage carries the n^-1 scaling.  Values between the
- * passes stay lazy ([0,4q) forward, [0,2q) inverse) in the result vector.
+ * column pass, which also applies the n^-1 scaling (through its twiddles).
+ * Values between the passes stay lazy ([0,4q) forward, [0,2q) inverse; [0,6q)
+ * and [0,3q) with the approximate quotient) in the result vector.
  * ====================================================================================== */
 #define FAST_THREADS 256
 /* Tuning knobs: tiles per thread (NP) and occupancy targets.
