@@ -66,7 +66,23 @@ def main():
         prod = oracle.elemmul(oracle.forward(xs[0], o2),
                               oracle.forward(xs[1], o2), q)
         assert np.array_equal(vs[2].to_host(), oracle.inverse(prod, o2))
-        for vec in vs:
+        # the reference's product sequence: two recorded forward transforms,
+        # the product fused into the in-place inverse (row pass / single pass)
+        fused0 = ctx.fused_products
+        ctx.forward_transform(vs[3], vs[3], t2)
+        ctx.forward_transform(vs[4], vs[4], t2)
+        ctx.elemmul(vs[3], vs[4], vs[0], q)
+        ctx.inverse_transform(vs[0], vs[0], t2)
+        prod = oracle.elemmul(oracle.forward(xs[3], o2),
+                              oracle.forward(xs[4], o2), q)
+        assert np.array_equal(vs[0].to_host(), oracle.inverse(prod, o2))
+        assert ctx.fused_products == fused0 + 1
+        # a record longer than the inline pointer table (device-side table)
+        more = [ctx.from_host(xs[i % 5]) for i in range(11)]
+        for vec in more:
+            ctx.forward_transform(vec, vec, t2)
+        assert np.array_equal(more[10].to_host(), oracle.forward(xs[0], o2))
+        for vec in vs + more:
             vec.destroy()
         t2.destroy()
     q = 769
