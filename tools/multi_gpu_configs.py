@@ -92,6 +92,41 @@ def main():
     emit({"config": "configs[2]: n=2^16, 32 limbs x batch 16, limb-sharded "
           "(%d limbs per GPU), forward+inverse" % own, "ms_per_step": ms,
           "ntt_per_s": 2 * limbs * batch / ms * 1e3, "round_trip_exact": ok})
+    if dist is not None:
+        # NOT on the hot path: the caller asks for the whole result on every
+        # GPU.  NCCL all-gather over NVLink straight out of / into the
+        # library's device vectors (zero-copy views), reported on its own.
+        import torch
+        ctx.forward_transform_rns(a, w, tabs, batch)
+        full = ctx.vector(world * host.size, zero=False)
+        ctx.sync()
+        src = torch.as_tensor(w, device=device)
+        dst = torch.as_tensor(full, device=device)
+        ev0, ev1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        for _ in range(3):
+            dist.all_gather_into_tensor(dst, src)
+        torch.cuda.synchronize()
+        barrier()
+        ev0.record()
+        for _ in range(10):
+            dist.all_gather_into_tensor(dst, src)
+        ev1.record()
+        torch.cuda.synchronize()
+        gms = slowest(ev0.elapsed_time(ev1) / 10)
+        got = full.to_host()[rank * host.size:(rank + 1) * host.size]
+        ok = all_ok(np.array_equal(got, w.to_host()))
+        emit({"config": "configs[2] result gather (optional, off the hot "
+              "path): NCCL all-gather of the limb shards, rank-major",
+              "ms": gms, "bytes_per_gpu": 8 * host.size,
+              "bytes_gathered": 8 * host.size * world,
+              "algbw_GBps": 8 * host.size * world / gms / 1e6,
+              "own_shard_intact": ok})
+        full.destroy()
+    if "--only-config2" in sys.argv:
+        ctx.destroy()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     a.destroy()
     w.destroy()
     for t in tabs:

@@ -185,6 +185,22 @@ class Vector:
     def dup(self):
         return Vector(self.ctx, lib().vkhel_vector_dup(self.handle))
 
+    @property
+    def device_ptr(self):
+        """raw device address (vkhel_vector_device_ptr): work recorded so far
+        is launched first; the caller orders its own use against the
+        context's stream (Context.sync)"""
+        return int(lib().vkhel_vector_device_ptr(self.handle) or 0)
+
+    @property
+    def __cuda_array_interface__(self):
+        """zero-copy view for libraries that speak the CUDA array interface
+        (e.g. torch.as_tensor(vec, device="cuda") for an NCCL gather); signed
+        64-bit, since torch has no unsigned 64-bit arithmetic -- the bits are
+        what is moved"""
+        return {"shape": (self.length,), "typestr": "<i8",
+                "data": (self.device_ptr, False), "version": 2}
+
     def copy_from_host(self, data):
         data = _as_u64(data)
         assert data.size >= self.length
