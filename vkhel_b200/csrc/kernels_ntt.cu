@@ -333,8 +333,22 @@ struct fast_pass {
 /* padded position of tile element i in a warp-group's exchange buffer: 4 words
  * of padding per 32 keep the strided reads of the second round conflict-free.
  * Additive over disjoint bit fields, like the tile index itself. */
+#ifndef ROWS_XPAD_HALF
+#define ROWS_XPAD_HALF 0
+#endif
 __host__ __device__ constexpr int xpad(int i) {
+#if ROWS_XPAD_HALF
+	/* 2 words per 16 instead of 4 per 32 (same buffer size): the 128-bit
+	 * accesses of the deepest round's layout -- 16 bytes at a 32-byte lane
+	 * stride -- then take 4 wavefronts instead of 8, everything else stays
+	 * minimal (tools/bank_model.py).  Measured: forward 0.3191 ms against
+	 * 0.3174, inverse 0.3454 against 0.3463 per 512 transforms of n = 2^16 --
+	 * nothing either way (the shared-memory pipe is at 18-20 %), so the
+	 * shipped padding stays */
+	return i + ((i >> 4) << 1);
+#else
 	return i + ((i >> 5) << 2);
+#endif
 }
 
 /* ---- programmatic dependent launch (PDL) ------------------------------------------
