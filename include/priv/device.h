@@ -60,6 +60,7 @@ struct device_ctx {
 	uint64_t deferred_batches;    /* indirect batches launched so far */
 	uint64_t deferred_transforms; /* transforms that went out in them */
 	uint64_t fused_products;      /* elemmul calls fused into the inverse that followed */
+	int stream_exposed;  /* vkhel_ctx_stream() handed the stream out: no more recording */
 };
 
 void device_ctx_init(struct device_ctx *dev, int device);

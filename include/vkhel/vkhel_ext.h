@@ -28,7 +28,11 @@ int vkhel_ctx_device(const struct vkhel_ctx *);
 /* block until everything enqueued on the context has completed (the reference
  * does this after every op, src/vector.c:327) */
 void vkhel_ctx_sync(struct vkhel_ctx *);
-/* the context's cudaStream_t, for callers that interleave their own work */
+/* the context's cudaStream_t, for callers that interleave their own work.
+ * What is recorded so far (see vkhel_ctx_deferred_stats) is launched, and from
+ * this call on the context records nothing: a caller holding the stream -- or
+ * a raw pointer from vkhel_vector_device_ptr, for operations on that vector --
+ * finds every later call already enqueued when it returns. */
 void *vkhel_ctx_stream(struct vkhel_ctx *);
 
 /* vkhel_ntt_tables_create (reference src/ntt_tables.c:65-80) with the four
@@ -102,8 +106,10 @@ void vkhel_timer_stop(struct vkhel_timer *);
 double vkhel_timer_elapsed_ms(struct vkhel_timer *);
 void vkhel_timer_destroy(struct vkhel_timer *);
 
-/* number of kernels this context has launched so far */
+/* number of kernels this context has launched so far (what is recorded is
+ * launched first; _noflush reads the counter without doing that) */
 uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *);
+uint64_t vkhel_ctx_launch_count_noflush(const struct vkhel_ctx *);
 /* vkhel_vector_forward_transform / _inverse_transform (one vector per call,
  * reference src/vector.c:513-657) are recorded and consecutive independent
  * calls with the same tables go out as one batched launch when the context is

@@ -136,6 +136,123 @@ def test_two_contexts_share_tables(ctx):
     tp.destroy()
 
 
+def _second_device():
+    """another GPU when the box has one, else the same device: the calls and
+    the expected results are the same either way"""
+    return 1 if vk.device_count() > 1 else 0
+
+
+def test_interleaved_contexts_on_one_thread(ctx):
+    """One host thread drives two contexts (two GPUs where there are two)
+    call by call: every entry point has to make its own context's device
+    current -- including the recorded transforms, the staging events of a
+    record longer than the inline pointer table (> 8 transforms) and the
+    product fused into the inverse transform."""
+    other = vk.Context(_second_device())
+    n, q = 1 << 12, params.P0
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(61)
+    x, y, z = (rand_mod(rng, n, q) for _ in range(3))
+    a0, b0, c0 = ctx.from_host(x), ctx.from_host(y), ctx.vector(n)
+    a1 = other.from_host(z)
+    # elemmul recorded on ctx, an operation on the other context in between,
+    # then the inverse that fuses with the product
+    ctx.elemmul(a0, b0, c0, q)
+    other.elemmul(a1, a1, a1, q)
+    ctx.inverse_transform(c0, c0, tp.lib)
+    other.forward_transform(a1, a1, tp.lib)
+    want_c = oracle.inverse(oracle.elemmul(x, y, q), tp.ora)
+    want_a1 = oracle.forward(oracle.elemmul(z, z, q), tp.ora)
+    assert np.array_equal(c0.to_host(), want_c)
+    assert np.array_equal(a1.to_host(), want_a1)
+    # a record of more than 8 transforms per context, the two interleaved
+    xs = [rand_mod(rng, n, q) for _ in range(24)]
+    v0 = [ctx.from_host(v) for v in xs[:12]]
+    v1 = [other.from_host(v) for v in xs[12:]]
+    for p, r in zip(v0, v1):
+        ctx.forward_transform(p, p, tp.lib)
+        other.inverse_transform(r, r, tp.lib)
+    for v, data in zip(v0, xs[:12]):
+        assert np.array_equal(v.to_host(), oracle.forward(data, tp.ora))
+    for v, data in zip(v1, xs[12:]):
+        assert np.array_equal(v.to_host(), oracle.inverse(data, tp.ora))
+    for v in [a0, b0, c0, a1] + v0 + v1:
+        v.destroy()
+    other.destroy()
+    tp.destroy()
+
+
+def test_copy_peer_between_contexts(ctx):
+    """vkhel_vector_copy_peer gathers shards that live in another context
+    (over NVLink when the contexts sit on different GPUs): ordered after the
+    source's pending work and before the destination's next use."""
+    other = vk.Context(_second_device())
+    n, q = 1 << 13, params.P0
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(62)
+    x, y = rand_mod(rng, n, q), rand_mod(rng, n, q)
+    local, remote = ctx.from_host(x), other.from_host(y)
+    ctx.forward_transform(local, local, tp.lib)
+    other.forward_transform(remote, remote, tp.lib)     # still only recorded
+    gathered = ctx.vector(2 * n + 5)
+    gathered.copy_peer(local, dst_offset=0)
+    gathered.copy_peer(remote, dst_offset=n)
+    gathered.copy_peer(remote, dst_offset=2 * n, src_offset=7, count=5)
+    # the source may be overwritten right away: the copy has been ordered
+    other.inverse_transform(remote, remote, tp.lib)
+    fy = oracle.forward(y, tp.ora)
+    got = gathered.to_host()
+    assert np.array_equal(got[:n], oracle.forward(x, tp.ora))
+    assert np.array_equal(got[n:2 * n], fy)
+    assert np.array_equal(got[2 * n:], fy[7:12])
+    assert np.array_equal(remote.to_host(), y)
+    # and the gathered vector is an ordinary vector of its context
+    ctx.inverse_transform_batch(gathered, gathered, tp.lib, 2)
+    assert np.array_equal(gathered.to_host()[:2 * n], np.concatenate([x, y]))
+    for v in (local, remote, gathered):
+        v.destroy()
+    other.destroy()
+    tp.destroy()
+
+
+def test_exposed_stream_stops_recording():
+    """Once vkhel_ctx_stream() or vkhel_vector_device_ptr() has handed out a
+    handle, the caller orders its own work by stream position, so every later
+    call must be enqueued when it returns: nothing is recorded any more."""
+    own = vk.Context(0)
+    n, q = 1 << 10, params.P0
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(63)
+    xs = [rand_mod(rng, n, q) for _ in range(6)]
+    vs = [own.from_host(v) for v in xs]
+    # before: a loop of transforms goes out as one recorded batch
+    for v in vs:
+        own.forward_transform(v, v, tp.lib)
+    own.sync()
+    assert own.deferred_stats == (1, 6)
+    # a vector whose pointer is out: transforms that touch it launch at once
+    assert vs[0].device_ptr != 0
+    l0 = own.launch_count
+    own.inverse_transform(vs[0], vs[0], tp.lib)
+    assert own.launch_count_noflush > l0
+    # the stream is out: nothing at all is recorded from now on
+    assert own.stream != 0
+    l0 = own.launch_count
+    for v in vs[1:]:
+        own.inverse_transform(v, v, tp.lib)
+        assert own.launch_count_noflush > l0
+        l0 = own.launch_count_noflush
+    own.elemmul(vs[0], vs[1], vs[2], q)
+    assert own.launch_count_noflush > l0
+    assert own.deferred_stats == (1, 6) and own.fused_products == 0
+    assert np.array_equal(vs[2].to_host(), oracle.elemmul(xs[0], xs[1], q))
+    assert np.array_equal(vs[3].to_host(), xs[3])
+    for v in vs:
+        v.destroy()
+    own.destroy()
+    tp.destroy()
+
+
 def test_table_lifetime_and_rns_plan_cache(ctx):
     """destroying and re-creating tables (possibly at the same address) must
     not resurrect a cached RNS plan: plans are keyed by table serials"""

@@ -78,6 +78,7 @@ SIGNATURES = {
     "vkhel_timer_elapsed_ms": (ctypes.c_double, [_vp]),
     "vkhel_timer_destroy": (None, [_vp]),
     "vkhel_ctx_launch_count": (_u64, [_vp]),
+    "vkhel_ctx_launch_count_noflush": (_u64, [_vp]),
     "vkhel_ctx_flush_l2": (None, [_vp]),
     "vkhel_ctx_flush": (None, [_vp]),
     "vkhel_ntt_tables_create_on": (_vp, [_vp, _u64, _u64, _u64]),
@@ -256,6 +257,17 @@ class Context:
     def sync(self):
         lib().vkhel_ctx_sync(self.handle)
 
+    @property
+    def stream(self):
+        """the context's cudaStream_t (vkhel_ctx_stream).  Handing it out
+        launches what is recorded and turns recording off for this context:
+        the caller now orders its own work by stream position."""
+        return int(lib().vkhel_ctx_stream(self.handle) or 0)
+
+    @property
+    def device(self):
+        return int(lib().vkhel_ctx_device(self.handle))
+
     def flush_l2(self):
         lib().vkhel_ctx_flush_l2(self.handle)
 
@@ -279,6 +291,11 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().vkhel_ctx_launch_count(self.handle))
+
+    @property
+    def launch_count_noflush(self):
+        """kernels launched so far; what is recorded stays recorded"""
+        return int(lib().vkhel_ctx_launch_count_noflush(self.handle))
 
     def vector(self, length, zero=True):
         return Vector(self, lib().vkhel_vector_create2(self.handle, length,

@@ -222,13 +222,21 @@ extern "C" void vkhel_ctx_sync(struct vkhel_ctx *ctx) {
 }
 
 extern "C" void *vkhel_ctx_stream(struct vkhel_ctx *ctx) {
-	/* the caller is about to order its own work against ours */
+	/* the caller is about to order its own work against ours: launch what is
+	 * recorded, and from now on record nothing (vector.cu, defer_transform) --
+	 * a cached stream handle must see every later call already enqueued */
+	ctx_enter(ctx);
 	defer_flush(ctx);
+	ctx->dev.stream_exposed = 1;
 	return ctx->dev.stream;
 }
 
 extern "C" uint64_t vkhel_ctx_launch_count(const struct vkhel_ctx *ctx) {
 	defer_flush((struct vkhel_ctx *) ctx);
+	return ctx->dev.launches;
+}
+
+extern "C" uint64_t vkhel_ctx_launch_count_noflush(const struct vkhel_ctx *ctx) {
 	return ctx->dev.launches;
 }
 
@@ -416,7 +424,7 @@ extern "C" void vkhel_host_free(void *ptr) {
 }
 
 /* ---- NTT table device mirrors -------------------------------------------------
- * Layout of one mirror: [limb_desc (64 B)][2n pairs of (w, w')][the first
+ * Layout of one mirror: [limb_desc (80 B)][2n pairs of (w, w')][the first
  * scaled_tw_pairs(n) inverse pairs times n^-1].  The tables object has no
  * context (reference src/ntt_tables.c:65-87), so the mirror is keyed by device
  * ordinal and freed in tables_destroy. */
@@ -456,7 +464,14 @@ static void fill_desc(const struct vkhel_ntt_tables *ntt, limb_desc *desc,
  * this platform (measured: 18-85 ms each, tools/tables_bench.py).  They are
  * taken from the device's default stream-ordered pool instead, which is kept
  * from trimming; ntt_tables_release_device returns them with cudaFree. */
+/* Tables are context-free and may be shared by contexts driven from different
+ * threads: creation, adoption and release of their device mirrors (and the
+ * one-time pool configuration) are serialised by this lock.  Recursive,
+ * because ensure_mirror allocates through ntt_tables_mirror_alloc. */
+static std::recursive_mutex g_mirror_lock;
+
 void *ntt_tables_mirror_alloc(struct vkhel_ctx *ctx, size_t bytes) {
+	std::lock_guard<std::recursive_mutex> guard(g_mirror_lock);
 	ctx_enter(ctx);
 	static bool configured[VKHEL_MAX_DEVICES];
 	const int device = ctx->dev.device;
@@ -476,6 +491,7 @@ void *ntt_tables_mirror_alloc(struct vkhel_ctx *ctx, size_t bytes) {
 static void *ensure_mirror(struct vkhel_ctx *ctx,
 		struct vkhel_ntt_tables *ntt) {
 	const int device = ctx->dev.device;
+	std::lock_guard<std::recursive_mutex> guard(g_mirror_lock);
 	if (ntt->dev_pairs[device]) {
 		return ntt->dev_pairs[device];
 	}
@@ -512,6 +528,7 @@ static void *ensure_mirror(struct vkhel_ctx *ctx,
  * of them and register the buffer as this device's mirror */
 void ntt_tables_adopt_mirror(struct vkhel_ctx *ctx,
 		struct vkhel_ntt_tables *ntt, char *dev_buf) {
+	std::lock_guard<std::recursive_mutex> guard(g_mirror_lock);
 	ctx_enter(ctx);
 	limb_desc desc;
 	fill_desc(ntt, &desc, (const ulonglong2 *) (dev_buf + sizeof(limb_desc)));
@@ -541,6 +558,7 @@ extern "C" void ntt_tables_release_device(struct vkhel_ntt_tables *ntt) {
 			defer_flush_tables(ctx, ntt);
 		}
 	}
+	std::lock_guard<std::recursive_mutex> guard(g_mirror_lock);
 	for (int device = 0; device < VKHEL_MAX_DEVICES; device++) {
 		if (!ntt->dev_pairs[device]) {
 			continue;

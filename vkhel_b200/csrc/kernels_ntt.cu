@@ -186,6 +186,15 @@ static void run_generic_pass(struct vkhel_ctx *ctx, gen_pass p) {
 	const u64 blocks = tile_groups << (low_bits - log2c);
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = sizeof(u64) << (log2g + p.k + log2c);
+	if (smem > 48 * 1024) {
+		/* the leading pass of n = 2^29, 2^30 on the fast path holds 2^13 / 2^14
+		 * points per tile: above the default dynamic shared memory limit */
+		VK_REQUIRE(smem <= ctx->dev.smem_optin,
+				"transform pass of 2^%u points does not fit in shared memory",
+				p.k);
+		CUDA_CHECK(cudaFuncSetAttribute(ntt_generic_kernel<INVERSE, STRICT>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
 	ntt_generic_kernel<INVERSE, STRICT>
 		<<<(unsigned) blocks, GEN_THREADS, smem, ctx_stream(ctx)>>>(p);
 	CUDA_CHECK(cudaGetLastError());

@@ -81,6 +81,9 @@ struct defer_queue {
 
 static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 	if (!ctx->dev.defer) {
+		/* the staging events belong to the context's device, whatever device
+		 * the calling thread last used */
+		enter(ctx);
 		defer_queue *dq = new defer_queue();
 		dq->mul.active = false;
 		dq->inverse = false;
@@ -253,6 +256,12 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 	static const bool off = getenv("VKHEL_NO_DEFER") != NULL;
 	struct vkhel_ctx *ctx = result->ctx;
 	if (off || !ntt_indirect_supported((unsigned) ntt->log2n, ntt->q)) {
+		return false;
+	}
+	/* A caller that holds the context's stream or a raw device pointer
+	 * orders its own work against ours by stream position: everything must be
+	 * enqueued when the call returns, so nothing is recorded any more. */
+	if (ctx->dev.stream_exposed || operand->exposed || result->exposed) {
 		return false;
 	}
 	defer_queue *dq = defer_get(ctx);
@@ -666,7 +675,10 @@ extern "C" void vkhel_vector_elemmul(
 	/* candidates for the fused inverse-of-product: a power-of-two length the
 	 * fast transform path covers */
 	const uint64_t len = result->length;
-	if (!off && len >= 8 && (len & (len - 1)) == 0 && mod < (1ull << 62)) {
+	const bool exposed = result->ctx->dev.stream_exposed || a->exposed
+		|| b->exposed || result->exposed;   /* see defer_transform */
+	if (!off && !exposed && len >= 8 && (len & (len - 1)) == 0
+			&& mod < (1ull << 62)) {
 		defer_flush(result->ctx);   /* what was recorded so far goes first */
 		defer_queue *dq = defer_get(result->ctx);
 		dq->mul.active = true;
@@ -788,6 +800,10 @@ extern "C" void vkhel_vector_forward_transform(
 			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
 	DBG_VEC("operand", operand);
 	check_ntt("forward_transform", operand, result, ntt, ntt->n);
+	/* a single thread may interleave contexts on different devices: every
+	 * CUDA call below (event creation, launches of a flushed record, the
+	 * fused product) has to find this context's device current */
+	enter(result->ctx);
 	if (ntt->n >= 2 && defer_transform(false, operand, result, ntt)) {
 		DBG_VEC("result", result);
 		return;
@@ -803,6 +819,7 @@ extern "C" void vkhel_vector_inverse_transform(
 			" omega: %" PRIu64 ")\n", ntt->n, ntt->q, ntt->w);
 	DBG_VEC("operand", operand);
 	check_ntt("inverse_transform", operand, result, ntt, ntt->n);
+	enter(result->ctx);
 	if (fuse_product_into_inverse(operand, result, ntt)) {
 		DBG_VEC("result", result);
 		return;
