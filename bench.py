@@ -3,21 +3,33 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Metric (BASELINE.json): 64-bit NTTs/sec at n=2^16.  Workload: the CKKS-like
-shape of BASELINE configs[2] -- n = 2^16, 32 RNS limbs (the 32 largest primes
-below 2^60 with q = 1 mod 2^18) x batch 16 = 512 polynomials = 256 MiB per
-GPU.  One step = one forward transform of the whole batch followed by one
-inverse transform of it (1024 NTTs).  With N GPUs every rank runs that
-workload on its own batch shard (weak scaling, no data-path collective; the
-reference has no multi-device path at all).
+Metric (BASELINE.json): 64-bit NTTs/sec at n=2^16.  Workload: BASELINE
+configs[2] -- n = 2^16, 32 RNS limbs (the 32 largest primes below 2^60 with
+q = 1 mod 2^18) x batch 16 = 512 polynomials = 256 MiB.  One step = one forward
+transform of the whole batch followed by one inverse transform of it (1024
+NTTs).
+
+N = 1: the whole workload on one GPU.  N > 1 (torchrun, one rank per GPU):
+the SAME total workload, LIMB-SHARDED as BASELINE names it -- rank r owns the
+contiguous limb range 32/N and uploads only those primes' tables; `value` is
+whole-job NTTs over the slowest rank's time: strong scaling, no data-path
+collective (the reference has no multi-device path at all).  The
+weak-scaling figure (every rank runs the full one-GPU workload) is the extra
+key `weak`.
 
 One JSON line is printed by rank 0.  `value` is measured with the inputs
 resident in HBM; `e2e` is the same metric through the C-ABI with host buffers
 (pinned host -> device copy of the step's input and device -> host copy of its
-result inside the timed region).  `roofline` places the step against the HBM
-roofline with the algorithmic 16*n bytes per NTT; `cpu_baseline` is the CPU
-oracle (a port of the reference's arithmetic; the reference has no CPU NTT of
-its own) on all host cores.
+result inside the timed region) next to `e2e_ceiling`, the box's own host <->
+device bandwidth measured in the same run without the library.  `roofline`
+places the step against the HBM roofline with the algorithmic 16*n bytes per
+NTT; `issue_roofline` against the integer (fmaheavy) pipe, with the pipe rates
+and the register-only butterfly rate measured in this run
+(vkhel_ctx_probe_int_peaks); `sustained` repeats the step for at least a second
+whatever --steps says; `cpu_baseline` is the CPU oracle (a port of the
+reference's arithmetic; the reference has no CPU NTT of its own) on all host
+cores.  What was timed is checked against the oracle outside the timed region
+(`checks`).
 """
 import argparse
 import json
@@ -39,29 +51,49 @@ BATCH = 16
 E2E_CHUNKS = 4
 POLYS = LIMBS * BATCH
 METRIC = "64-bit NTTs/sec at n=2^16"
-# measured per-GPU integer peaks (profiles/r01_bfly_bench.txt)
-BFLY_PEAK_G = 1038.0         # lazy Harvey butterflies/s, best compiled form (v19)
-BFLY_MULT_BOUND_G = 1163.0   # 16 fmaheavy slots per butterfly, nothing else
-# DRAM bytes of one step as measured by ncu (profiles/r01_ntt_traffic.json,
-# made by tools/ncu_traffic.py from a --cache-control none launch list of this
-# very command); the constant is the value of that file at commit time
+SUSTAINED_SECONDS = 1.0
+# DRAM bytes of one step as measured by ncu (profiles/*_ntt_traffic.json, made
+# by tools/ncu_traffic.py from a --cache-control none launch list of this very
+# command); the constant is the fallback when no such file travels with the run
 NCU_TRAFFIC_BYTES_PER_STEP = 1180000000
 NCU_TRAFFIC_SOURCE = ("ncu --cache-control none --metrics dram__bytes_*, "
-                      "profiles/r01_ntt_traffic.json")
+                      "profiles/%s")
 
 
 def ncu_traffic():
-    path = os.path.join(ROOT, "profiles", "r01_ntt_traffic.json")
-    try:
-        with open(path) as f:
-            return int(json.load(f)["bytes_per_step"]), NCU_TRAFFIC_SOURCE
-    except (OSError, KeyError, ValueError):
-        return NCU_TRAFFIC_BYTES_PER_STEP, NCU_TRAFFIC_SOURCE
+    for name in ("r02_ntt_traffic.json", "r01_ntt_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return (int(json.load(f)["bytes_per_step"]),
+                        NCU_TRAFFIC_SOURCE % name)
+        except (OSError, KeyError, ValueError):
+            continue
+    return NCU_TRAFFIC_BYTES_PER_STEP, NCU_TRAFFIC_SOURCE % "(constant)"
 
 
 WORKLOAD = ("n=2^16 negacyclic NTT, 32 RNS limbs (60-bit primes) x batch 16 "
-            "= 512 polys = 256 MiB per GPU (BASELINE configs[2] shape); "
+            "= 512 polys = 256 MiB in all (BASELINE configs[2]); "
             "step = forward + inverse of the whole batch")
+
+
+def workload_config(world):
+    """the `config` object of BOTH arms: it names the workload, nothing that
+    differs between the arms or between runs"""
+    if world == 1:
+        parallelism = "single GPU, all 32 limbs"
+    else:
+        parallelism = ("limb-sharded %d/%d: each of %d GPUs owns %d limbs x "
+                       "batch %d, fixed total, no collective"
+                       % (LIMBS, world, world, LIMBS // world, BATCH))
+    return {
+        "workload": WORKLOAD, "n": N, "limbs": LIMBS, "batch": BATCH,
+        "ntts_per_step": 2 * POLYS, "parallelism": parallelism,
+        "l2": "working set 512 MiB per step over all GPUs, read and written "
+              "once per pass; at N <= 2 larger than the 126 MB L2, no flush; "
+              "at N >= 4 the shard (<= 64 MiB) stays L2-resident between "
+              "steps, as it would in an application that keeps its limbs on "
+              "the GPU",
+    }
 
 
 class c_stdout_to_stderr:
@@ -81,12 +113,13 @@ class c_stdout_to_stderr:
 
 # ---- clocks --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region.
+    """nvidia-smi clocks / throttle reasons during the timed regions.
 
-    One long-lived `nvidia-smi -lms` process, started well before the timed
-    region (its start-up takes a few hundred milliseconds on a fresh box);
-    every line is stamped on arrival and stop(t0, t1) keeps the samples that
-    fall inside the timed region [t0, t1]."""
+    One long-lived `nvidia-smi -lms` process, started well before the first
+    timed region (its start-up takes a few hundred milliseconds on a fresh
+    box); every line is stamped on arrival, window(t0, t1) summarises the
+    samples that fall inside [t0, t1] and stop(t0, t1) does the same and ends
+    the process."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,"
              "clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,"
@@ -122,19 +155,18 @@ class ClockSampler:
         while self.proc and not self.lines and time.perf_counter() < t_end:
             time.sleep(0.01)
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
                     "note": "nvidia-smi unavailable"}
+        # the last readings of the window are still on their way
         time.sleep(2.5 * self.PERIOD_MS / 1e3)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
 
         def collect(lo, hi):
             sm, smax, reasons, power = [], [], set(), []
-            for stamp, line in self.lines:
+            for stamp, line in list(self.lines):
                 if stamp < lo or stamp > hi:
                     continue
                 parts = [p.strip() for p in line.split(",")]
@@ -158,8 +190,8 @@ class ClockSampler:
         note = "samples inside the timed region"
         if not sm:
             # timed region shorter than the sampling period: the nearest
-            # samples around it (the GPU is under the same load: warm-up steps
-            # before, the forward-only / inverse-only timing after)
+            # samples around it (the GPU is under the same load before and
+            # after: warm-up steps, the sustained run)
             sm, smax, reasons, power = collect(t0 - 0.2, t1 + 0.2)
             note = "timed region shorter than one sampling period: samples within 0.2 s of it"
         return {"sm_mhz": float(np.median(sm)) if sm else None,
@@ -168,15 +200,31 @@ class ClockSampler:
                 "samples": len(sm), "period_ms": self.PERIOD_MS,
                 "reasons": sorted(reasons), "note": note}
 
+    def stop(self, t0, t1):
+        out = self.window(t0, t1)
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+        return out
+
 
 # ---- workload ------------------------------------------------------------------------
-def make_inputs(primes, seed):
+def poly_seed(batch_entry, limb):
+    """the same polynomial whatever the sharding: seeded by its position in
+    the [batch][32 limbs] layout (xorshift64, coefficients mod q)"""
+    return 0x9E3779B97F4A7C15 + 2 * 1000 + batch_entry * LIMBS + limb
+
+
+def make_inputs(primes, lo, hi):
+    """[BATCH][hi - lo][N]: the limbs [lo, hi) of the workload"""
     from vkhel_b200 import params
-    out = np.empty(POLYS * N, np.uint64)
-    for p in range(POLYS):
-        q = primes[p % LIMBS]
-        out[p * N:(p + 1) * N] = params.xorshift64_stream(
-            0x9E3779B97F4A7C15 + seed * 1000 + p, N, q)
+    own = hi - lo
+    out = np.empty(BATCH * own * N, np.uint64)
+    for b in range(BATCH):
+        for l in range(lo, hi):
+            p = b * own + (l - lo)
+            out[p * N:(p + 1) * N] = params.xorshift64_stream(
+                poly_seed(b, l), N, primes[l])
     return out
 
 
@@ -190,79 +238,97 @@ def measured_peaks():
 
 
 # ---- CPU arm -------------------------------------------------------------------------
-def cpu_arm(primes, psis, target_seconds, sample_polys=None):
-    """fwd+inv on a bounded sample with the CPU oracle on all host cores.
-    Returns (ntts_per_sec, cores, sample description, seconds)."""
-    import oracle
-    cores = os.cpu_count() or 1
-    limbs = min(LIMBS, 4)
-    tables = [oracle.Tables(N, primes[l], psis[l]) for l in range(limbs)]
-    from vkhel_b200 import params
-    one = params.xorshift64_stream(1, N, primes[0])
-    t0 = time.perf_counter()
-    oracle.inverse(oracle.forward(one, tables[0]), tables[0])
-    t_one = time.perf_counter() - t0            # 2 NTTs, single thread
-    if sample_polys is None:
-        sample_polys = int(max(cores, min(POLYS, cores * target_seconds / t_one)))
-        sample_polys -= sample_polys % limbs or 0
-        sample_polys = max(sample_polys, limbs)
-    x = np.concatenate([params.xorshift64_stream(100 + p, N, primes[p % limbs])
-                        for p in range(sample_polys)])
+class CpuArm:
+    """the CPU oracle on all host cores over all 32 limbs of the workload;
+    a step transforms `sample_polys` polynomials forward and back"""
+
+    def __init__(self):
+        import oracle
+        from vkhel_b200 import params
+        self.oracle = oracle
+        self.cores = os.cpu_count() or 1
+        self.primes = params.ntt_primes(LIMBS)
+        psis = [params.find_psi(N, q) for q in self.primes]
+        self.tables = [oracle.Tables(N, q, w) for q, w in zip(self.primes, psis)]
+        one = params.xorshift64_stream(1, N, self.primes[0])
+        t0 = time.perf_counter()
+        oracle.inverse(oracle.forward(one, self.tables[0]), self.tables[0])
+        self.t_pair = time.perf_counter() - t0          # 2 NTTs, single thread
+
+    def sample(self, polys):
+        """`polys` polynomials in the workload's [batch][32 limbs] order
+        (polynomial p uses limb p % 32), a multiple of 32"""
+        from vkhel_b200 import params
+        polys = max(LIMBS, polys - polys % LIMBS)
+        polys = min(polys, POLYS)
+        x = np.concatenate([params.xorshift64_stream(
+            poly_seed(p // LIMBS, p % LIMBS), N, self.primes[p % LIMBS])
+            for p in range(polys)])
+        return polys, x
+
+    def step(self, x):
+        fwd = self.oracle.forward_batch(x, self.tables, threads=self.cores)
+        return self.oracle.inverse_batch(fwd, self.tables, threads=self.cores)
+
+    def polys_for(self, seconds):
+        """sample size whose step takes about `seconds` on all cores"""
+        return int(self.cores * seconds / self.t_pair)
+
+
+def cpu_baseline(target_seconds):
+    """fwd+inv on a bounded sample of the workload (all 32 limbs), repeated
+    until about `target_seconds` have passed"""
+    arm = CpuArm()
+    polys, x = arm.sample(arm.polys_for(target_seconds / 4))
     reps = 0
     t0 = time.perf_counter()
     while True:
-        fwd = oracle.forward_batch(x, tables, threads=cores)
-        back = oracle.inverse_batch(fwd, tables, threads=cores)
+        back = arm.step(x)
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= target_seconds or reps >= 64:
             break
     assert np.array_equal(back, x)
-    sample = ("%d x (%d polys of n=2^16 over %d limbs, forward+inverse), "
-              "OpenMP over polynomials" % (reps, sample_polys, limbs))
-    return 2 * sample_polys * reps / dt, cores, sample, dt, (tables, x)
+    sample = ("%d x (%d polys of n=2^16 over all %d limbs, forward+inverse), "
+              "OpenMP over polynomials" % (reps, polys, LIMBS))
+    return {"value": 2 * polys * reps / dt, "unit": "NTT/s",
+            "cores": arm.cores, "kind": "port", "sample": sample,
+            "seconds": dt}
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU arithmetic (the oracle port: the
     reference's transform exists only as GLSL and no Vulkan stack is in this
-    image) on all host cores, each step a bounded sample of the workload."""
+    image) on all host cores, on the same workload -- all 32 limbs -- each
+    step a bounded sample of it."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from vkhel_b200 import params
-    import oracle
-    primes = params.ntt_primes(LIMBS)
-    psis = [params.find_psi(N, q) for q in primes[:4]]
-    cores = os.cpu_count() or 1
-    rate, cores, sample, dt, (tables, x) = cpu_arm(primes, psis, 2.0)
-    # one step = the per-GPU batch (512 polynomials) when K + W steps of it
-    # fit in about two minutes, else the largest sample that does
-    limbs = len(tables)
-    budget_polys = rate / 2 * 120.0 / (args.steps + max(args.warmup, 1))
-    sample_polys = int(min(x.size // N, max(budget_polys, cores, limbs)))
-    sample_polys = max(sample_polys - sample_polys % limbs, limbs)
-    x = x[:sample_polys * N]
-    sample = ("%d polys of n=2^16 over %d limbs, forward+inverse, OpenMP over "
-              "polynomials" % (sample_polys, limbs))
-    for _ in range(max(args.warmup - 1, 0)):
-        oracle.inverse_batch(oracle.forward_batch(x, tables, threads=cores),
-                             tables, threads=cores)
+    arm = CpuArm()
+    # one step = the whole batch (512 polynomials) when K + W steps of it fit
+    # in about two minutes, else the largest whole-basis sample that does
+    budget = 120.0 / (args.steps + max(args.warmup, 1))
+    polys, x = arm.sample(arm.polys_for(budget))
+    sample = ("%d of the %d polys (n=2^16, all %d limbs), forward+inverse, "
+              "OpenMP over polynomials" % (polys, POLYS, LIMBS))
+    for _ in range(max(args.warmup, 0)):
+        arm.step(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.inverse_batch(oracle.forward_batch(x, tables, threads=cores),
-                             tables, threads=cores)
+        back = arm.step(x)
     elapsed = time.perf_counter() - t0
-    value = 2 * sample_polys * args.steps / elapsed
+    assert np.array_equal(back, x)
+    value = 2 * polys * args.steps / elapsed
     line = {
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "NTT/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "sample": sample + " per step"},
-        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": cores,
+        "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": arm.cores,
                          "kind": "port", "sample": sample + " per step"},
         "e2e": {"value": value, "unit": "NTT/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -298,9 +364,45 @@ def bind_near_gpu(device):
 
 
 # ---- GPU arm -------------------------------------------------------------------------
+def issue_roofline(peaks, bfly_rate_g, kernel_clock_mhz):
+    """the binding roofline: butterflies/s against the fmaheavy pipe.  `peaks`
+    are this run's vkhel_ctx_probe_int_peaks: instruction rates per clock per
+    SM and the library's butterfly on registers only."""
+    sms = peaks["sm_count"]
+    ghz = (kernel_clock_mhz or peaks["sm_clock_mhz"]) / 1e3
+    # issue slots of the pipe per instruction, in units of one IMAD
+    slot_wide = peaks["imad"] / peaks["imad_wide"]
+    slot_hi = peaks["imad"] / peaks["imad_hi"]
+    # a lazy butterfly is one Shoup product with the approximate quotient:
+    # 4 IMAD.WIDE + 1 IMAD.HI + 4 IMAD (modarith.cuh, shoup_chain<true>)
+    slots = 4 * slot_wide + slot_hi + 4
+    mult_bound = peaks["imad"] / slots * sms * ghz            # G butterflies/s
+    reg_only = 0.5 * (peaks["bfly_forward"] + peaks["bfly_inverse"]) * sms * ghz
+    return {
+        "bound": "imad (fmaheavy pipe)", "achieved": bfly_rate_g,
+        "peak": mult_bound, "unit": "G butterflies/s",
+        "frac": bfly_rate_g / mult_bound,
+        "peak_source": "measured in this run: IMAD %.1f, IMAD.WIDE %.1f, "
+                       "IMAD.HI %.1f thread-instructions/clk/SM; a butterfly's "
+                       "multiplies (4 wide + 1 hi + 4 narrow) = %.1f IMAD "
+                       "slots; x %d SMs x %.3f GHz (SM clock of the timed "
+                       "region)" % (peaks["imad"], peaks["imad_wide"],
+                                    peaks["imad_hi"], slots, sms, ghz),
+        "slots_per_butterfly": slots,
+        "register_only_butterfly_rate": reg_only,
+        "frac_of_register_only": bfly_rate_g / reg_only,
+        "register_only_source": "the library's ct_lazy3 / gs_lazy3 on "
+                                "register operands, no memory: %.2f / %.2f per "
+                                "clk per SM, measured in this run"
+                                % (peaks["bfly_forward"], peaks["bfly_inverse"]),
+        "probe_clock_mhz": peaks["sm_clock_mhz"],
+        "alu_pipe_lop3_per_clk_sm": peaks["lop3"],
+    }
+
+
 def run_native_arm(args):
     import vkhel_b200 as vk
-    from vkhel_b200 import params
+    from vkhel_b200 import params, shard
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -312,6 +414,9 @@ def run_native_arm(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl",
                                 device_id=torch.device("cuda", local_rank))
+        if LIMBS % world:
+            raise SystemExit("bench.py: %d limbs do not shard evenly over %d "
+                             "GPUs" % (LIMBS, world))
 
     if vk.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; vkhel has no CPU path "
@@ -326,21 +431,33 @@ def run_native_arm(args):
         if dist is None:
             return value
         import torch
-        from vkhel_b200 import shard
         return shard.max_over_ranks(value, dist,
                                     torch.device("cuda", local_rank))
 
+    def sum_over_ranks(value):
+        if dist is None:
+            return value
+        import torch
+        t = torch.tensor([float(value)], dtype=torch.float64,
+                         device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     primes = params.ntt_primes(LIMBS)
-    psis = [params.find_psi(N, q) for q in primes]
+    lo, hi = shard.limb_shard(LIMBS, world, rank)
+    own = hi - lo                                   # limbs of this rank
+    own_polys = own * BATCH
     with c_stdout_to_stderr():
         ctx = vk.Context(local_rank)
-    tables = [vk.NttTables(N, q, w) for q, w in zip(primes, psis)]
+    # only this rank's primes: tables are generated on (and for) its GPU
+    tables = [vk.NttTables(N, q, params.find_psi(N, q), ctx=ctx)
+              for q in primes[lo:hi]]
 
-    host_in = vk.host_alloc(POLYS * N)
-    host_out = vk.host_alloc(POLYS * N)
-    host_in.array[:] = make_inputs(primes, rank)
-    data = ctx.vector(POLYS * N, zero=False)
-    work = ctx.vector(POLYS * N, zero=False)
+    host_in = vk.host_alloc(own_polys * N)
+    host_out = vk.host_alloc(own_polys * N)
+    host_in.array[:] = make_inputs(primes, lo, hi)
+    data = ctx.vector(own_polys * N, zero=False)
+    work = ctx.vector(own_polys * N, zero=False)
     data.upload(host_in)
     ctx.sync()
 
@@ -348,12 +465,12 @@ def run_native_arm(args):
         ctx.forward_transform_rns(data, work, tables, BATCH)
         ctx.inverse_transform_rns(work, work, tables, BATCH)
 
-    # end-to-end path: the batch moves in E2E_CHUNKS slices of whole batch
+    # end-to-end path: the shard moves in E2E_CHUNKS slices of whole batch
     # entries, each slice on its own device vector, two sets of slices used
     # alternately: upload (H2D copy stream), both transforms (compute stream)
     # and download (D2H copy stream) of different slices overlap.
     chunk_batch = BATCH // E2E_CHUNKS
-    chunk_elems = chunk_batch * LIMBS * N
+    chunk_elems = chunk_batch * own * N
     slices = [[ctx.vector(chunk_elems, zero=False) for _ in range(E2E_CHUNKS)]
               for _ in range(2)]
     e2e_state = {"step": 0}
@@ -369,7 +486,6 @@ def run_native_arm(args):
                        host_offset=c * chunk_elems)
 
     timer = ctx.timer()
-
     timed_window = [0.0, 0.0]   # host clock around the last timed region
 
     def timed(step_fn, steps, warmup):
@@ -391,7 +507,7 @@ def run_native_arm(args):
 
     # bring the GPU out of its idle clocks before anything is timed: an idle
     # B200 sits at 120 MHz and needs tens of milliseconds of load to reach its
-    # boost clock; W steps of 0.8 ms are too short for that
+    # boost clock; W steps of well under a millisecond are too short for that
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -409,17 +525,34 @@ def run_native_arm(args):
             ctx.sync()
     barrier()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
-    window = tuple(timed_window)
-    # the same load continues while the last samples arrive
-    for _ in range(60):
-        step_resident()
-    ctx.sync()
-    clocks = sampler.stop(*window) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    clocks = sampler.window(*timed_window) if rank == 0 else None
+    # the sustained figure: the same step for at least SUSTAINED_SECONDS,
+    # whatever --steps was, with its own clock and power samples
+    sus_steps = max(args.steps, int(SUSTAINED_SECONDS / (ms_per_step * 1e-3)) + 1)
+    ms_sus, _ = timed(step_resident, sus_steps, 0)
+    sus_clocks = sampler.stop(*timed_window) if rank == 0 else None
 
-    # correctness of what was just timed: the round trip returns the input
+    # ---- what was just timed, against the oracle (outside the timed region):
+    # the forward transform of one polynomial per limb of the shard, bit for
+    # bit, and the round trip of the whole shard
+    import oracle
+    ctx.forward_transform_rns(data, work, tables, BATCH)
     work.download(host_out)
     ctx.sync()
-    ok = bool(np.array_equal(host_out.array, host_in.array))
+    checked, parity_ok = 0, True
+    for l in range(own):
+        b = (lo + l) % BATCH                        # a different entry per limb
+        p = b * own + l
+        ora = oracle.Tables(N, primes[lo + l], tables[l].w)
+        want = oracle.forward(host_in.array[p * N:(p + 1) * N], ora)
+        parity_ok = parity_ok and bool(
+            np.array_equal(host_out.array[p * N:(p + 1) * N], want))
+        checked += 1
+    ctx.inverse_transform_rns(work, work, tables, BATCH)
+    work.download(host_out)
+    ctx.sync()
+    ok = parity_ok and bool(np.array_equal(host_out.array, host_in.array))
 
     # forward-only and inverse-only durations (per direction roofline)
     def fwd_only():
@@ -436,10 +569,53 @@ def run_native_arm(args):
     ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
     ok = ok and bool(np.array_equal(host_out.array, host_in.array))
 
+    # the box's own host <-> device bandwidth, all ranks copying at once,
+    # without the library (tools/pcie_probe.py: plain cudaMemcpyAsync)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import pcie_probe
+        pcie = pcie_probe.measure(local_rank, mib=128, reps=4, barrier=barrier)
+        both = sum_over_ranks(pcie["both_each_GBps"])
+        ceiling = {
+            "value": both * 1e9 / (256 * 1024), "unit": "NTT/s",
+            "aggregate_both_directions_each_GBps": both,
+            "aggregate_h2d_alone_GBps": sum_over_ranks(pcie["h2d_alone_GBps"]),
+            "aggregate_d2h_alone_GBps": sum_over_ranks(pcie["d2h_alone_GBps"]),
+            "how": "tools/pcie_probe.py: cudaMemcpyAsync of 128 MiB pinned "
+                   "buffers on every rank at once, no library; one NTT moves "
+                   "256 KiB each way while both directions are busy",
+        }
+    except Exception as err:    # noqa: BLE001 (probe is best effort)
+        sum_over_ranks(0.0), sum_over_ranks(0.0), sum_over_ranks(0.0)
+        ceiling = {"value": None, "unit": "NTT/s", "error": str(err)[:120]}
+
+    # the weak-scaling figure: every rank runs the whole one-GPU workload
+    weak = None
+    if world > 1:
+        wtables = [vk.NttTables(N, q, params.find_psi(N, q), ctx=ctx)
+                   for q in primes]
+        wdata = ctx.vector(POLYS * N, zero=False)
+        wwork = ctx.vector(POLYS * N, zero=False)
+        ctx.forward_transform_rns(wdata, wdata, wtables, BATCH)   # any residues
+
+        def step_weak():
+            ctx.forward_transform_rns(wdata, wwork, wtables, BATCH)
+            ctx.inverse_transform_rns(wwork, wwork, wtables, BATCH)
+
+        ms_weak, _ = timed(step_weak, args.steps, max(args.warmup, 3))
+        weak = {"value": world * 2 * POLYS / (ms_weak / args.steps * 1e-3),
+                "unit": "NTT/s", "scaling": "weak",
+                "ms_per_step": ms_weak / args.steps,
+                "workload": "every GPU runs all 32 limbs x batch 16"}
+        for v in (wdata, wwork):
+            v.destroy()
+        for t in wtables:
+            t.destroy()
+
     # the same trip through the reference's 18 calls only (one vector per
     # polynomial, pageable host memory): copy_from_host, forward_transform,
-    # inverse_transform, map (read the result), unmap.  A bounded sample of
-    # the batch: LEGACY_POLYS polynomials over the first limbs.
+    # inverse_transform, map (read the result), unmap.  A bounded sample:
+    # LEGACY_POLYS polynomials over this rank's limbs.
     legacy_polys = 64
     legacy_vecs = [ctx.vector(N, zero=False) for _ in range(legacy_polys)]
     legacy_in = np.array(host_in.array[:legacy_polys * N])   # pageable copy
@@ -449,58 +625,76 @@ def run_native_arm(args):
         for p, v in enumerate(legacy_vecs):
             v.copy_from_host(legacy_in[p * N:(p + 1) * N])
         for p, v in enumerate(legacy_vecs):
-            ctx.forward_transform(v, v, tables[p % LIMBS])
+            ctx.forward_transform(v, v, tables[p % own])
         for p, v in enumerate(legacy_vecs):
-            ctx.inverse_transform(v, v, tables[p % LIMBS])
+            ctx.inverse_transform(v, v, tables[p % own])
         for p, v in enumerate(legacy_vecs):
             legacy_out[p * N:(p + 1) * N] = v.to_host()
 
     step_legacy()
     ctx.sync()
+    barrier()
     t_legacy = time.perf_counter()
     legacy_steps = 3
     for _ in range(legacy_steps):
         step_legacy()
     ctx.sync()
-    t_legacy = (time.perf_counter() - t_legacy) / legacy_steps
+    t_legacy = max_over_ranks((time.perf_counter() - t_legacy) / legacy_steps)
     ok = ok and bool(np.array_equal(legacy_out, legacy_in))
     legacy_value = world * 2 * legacy_polys / t_legacy
 
-    ntts_per_step = 2 * POLYS
-    ms_per_step = ms_total / args.steps
-    value = world * ntts_per_step / (ms_per_step * 1e-3)
-    e2e_value = world * ntts_per_step / (ms_e2e / e2e_steps * 1e-3)
+    peaks = ctx.probe_int_peaks() if rank == 0 else None
+    all_ok = max_over_ranks(0.0 if ok else 1.0) == 0.0
+    checked_total = int(sum_over_ranks(checked))
+
+    ntts_per_step = 2 * POLYS                       # whole job, every N
+    value = ntts_per_step / (ms_per_step * 1e-3)
+    sus_value = ntts_per_step / (ms_sus / sus_steps * 1e-3)
+    e2e_value = ntts_per_step / (ms_e2e / e2e_steps * 1e-3)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        peak *= world
         algo_bytes = 16 * N * ntts_per_step
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "NTT/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD, "n": N, "limbs": LIMBS,
-                "batch_per_gpu": BATCH, "parallelism": "batch-sharded x%d, "
-                "no collective" % world,
-                "l2": "working set 512 MiB per step > 126 MB L2, no flush",
-                "round_trip_exact": ok,
+            "config": workload_config(world),
+            "checks": {
+                "all_ranks_exact": all_ok,
+                "parity_checked_polys": checked_total,
+                "what": "forward transform of one polynomial per limb of "
+                        "every shard bit-exact against the CPU oracle; round "
+                        "trip of every shard (resident, e2e and reference-API "
+                        "paths) returns the input",
                 "host_numa_binding": numa,
             },
+            "sustained": {
+                "value": sus_value, "unit": "NTT/s", "steps": sus_steps,
+                "seconds": ms_sus * 1e-3,
+                "ms_per_step": ms_sus / sus_steps, "clocks": sus_clocks},
             "e2e": {"value": e2e_value, "unit": "NTT/s",
                     "h2d_bytes_per_step": POLYS * N * 8,
                     "d2h_bytes_per_step": POLYS * N * 8,
                     "steps": e2e_steps,
-                    "path": "per 64 MiB slice: vkhel_vector_upload (pinned) "
-                            "-> forward_transform_rns -> "
+                    "frac_of_ceiling": (e2e_value / ceiling["value"]
+                                        if ceiling.get("value") else None),
+                    "path": "per slice of 4 batch entries: vkhel_vector_upload "
+                            "(pinned) -> forward_transform_rns -> "
                             "inverse_transform_rns -> vkhel_vector_download;"
                             " copies on the context's H2D/D2H streams "
                             "overlap with each other and with compute"},
+            "e2e_ceiling": ceiling,
             "e2e_reference_api": {
                 "value": legacy_value, "unit": "NTT/s",
-                "sample": "%d polynomials, one vkhel_vector each" % legacy_polys,
+                "sample": "%d polynomials per rank, one vkhel_vector each"
+                          % legacy_polys,
                 "path": "the reference's 18 entry points only, pageable host "
                         "memory: vkhel_vector_copy_from_host -> "
                         "vkhel_vector_forward_transform -> "
@@ -514,11 +708,12 @@ def run_native_arm(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic()[0],
-                "traffic_source": ncu_traffic()[1] + " (two passes per "
+                "traffic": traffic if world == 1 else None,
+                "traffic_source": traffic_src + " (two passes per "
                                   "transform, the intermediate stays in L2: "
-                                  "limb slices on two streams)",
-                "peak_source": peak_src,
+                                  "limb slices on two streams; N = 1)",
+                "peak_source": peak_src + (" x %d GPUs" % world
+                                           if world > 1 else ""),
                 "kernel": "whole step (forward + inverse NTT, all passes)",
                 "algorithmic_bytes_per_step": algo_bytes,
                 "forward_ms": ms_fwd / args.steps,
@@ -527,26 +722,16 @@ def run_native_arm(args):
                 "inverse_GBps": 16 * N * POLYS / (ms_inv / args.steps * 1e-3) / 1e9,
             },
         }
-        # the binding roofline: integer (fmaheavy-pipe) butterfly rate,
-        # measured by tools/bfly_bench.cu on this pool (profiles/r01_bfly_bench.txt)
+        if weak:
+            line["weak"] = weak
+        # the binding roofline: integer (fmaheavy-pipe) butterfly rate per GPU
         bfly_per_step = ntts_per_step * (N // 2) * LOG2N
-        bfly_rate = bfly_per_step / (ms_per_step * 1e-3) / 1e9
-        line["issue_roofline"] = {
-            "bound": "imad (fmaheavy pipe)", "achieved": bfly_rate,
-            "peak": BFLY_PEAK_G, "unit": "G butterflies/s",
-            "frac": bfly_rate / BFLY_PEAK_G,
-            "peak_source": "tools/bfly_bench.cu v19 (the library's butterfly: "
-                           "borrow-chain csub, approximate-quotient Shoup "
-                           "product as one PTX mad chain; twiddles in uniform "
-                           "registers, no memory): 3.57 per clk per SM x 148 "
-                           "SMs x 1.965 GHz",
-            "pure_multiplier_bound": BFLY_MULT_BOUND_G,
-        }
+        bfly_rate = bfly_per_step / (ms_per_step * 1e-3) / 1e9 / world
+        line["issue_roofline"] = issue_roofline(
+            peaks, bfly_rate, clocks.get("sm_mhz") if clocks else None)
+        line["issue_roofline"]["per"] = "GPU"
         if world == 1 and not args.no_cpu:
-            rate, cores, sample, dt, _ = cpu_arm(primes, psis[:4], 12.0)
-            line["cpu_baseline"] = {"value": rate, "unit": "NTT/s",
-                                    "cores": cores, "kind": "port",
-                                    "sample": sample, "seconds": dt}
+            line["cpu_baseline"] = cpu_baseline(12.0)
         print(json.dumps(line))
 
     timer.destroy()
@@ -559,8 +744,8 @@ def run_native_arm(args):
     ctx.destroy()
     if dist is not None:
         dist.destroy_process_group()
-    if not ok:
-        raise SystemExit("bench.py: round trip mismatch -- result invalid")
+    if not all_ok:
+        raise SystemExit("bench.py: parity / round trip mismatch -- result invalid")
 
 
 def main():

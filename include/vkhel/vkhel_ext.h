@@ -126,6 +126,19 @@ void vkhel_ctx_flush(struct vkhel_ctx *);
  * multiplication happens inside the inverse transform's first pass; any other
  * call launches the product first.  Number of products fused so far: */
 uint64_t vkhel_ctx_fused_products(const struct vkhel_ctx *);
+/* Integer-pipe probes on the context's device (probe.cu): the denominators of
+ * the transform's binding roofline, measured in the run that reports them.
+ * Writes up to `count` doubles and returns how many:
+ *   [0] SM count                      [1] SM clock during the probes, MHz
+ *   [2] IMAD        thread-instructions per clock per SM (mad.lo.u32)
+ *   [3] IMAD.WIDE   (mad.wide.u32)    [4] IMAD.HI (mad.hi.u32)
+ *   [5] LOP3        (the ALU pipe)
+ *   [6] forward / [7] inverse lazy butterflies per clock per SM, the library's
+ *       own butterfly code on register operands only
+ *   [8] SHF (funnel shift)   [9] IADD3 with three addends
+ *   [10] 64-bit addition of three values (IADD3 + IADD3.X, two carries)
+ *   [11] 64-bit add + conditional subtraction (the butterflies' csub) */
+int vkhel_ctx_probe_int_peaks(struct vkhel_ctx *, double *out, int count);
 /* write a buffer larger than L2 so the next kernel starts cold */
 void vkhel_ctx_flush_l2(struct vkhel_ctx *);
 

@@ -35,8 +35,11 @@ def test_reference_arm_prints_the_contract_line():
     assert (d["n_gpus"], d["steps"], d["warmup"]) == (1, 2, 1)
     assert d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["dtype"] == "u64" and d["data"] == "synthetic"
-    assert d["config"]["workload"] == bench.WORKLOAD
+    # the reference arm names the workload exactly like the native arm does
+    assert d["config"] == bench.workload_config(1)
+    assert d["config"]["limbs"] == 32 and d["config"]["batch"] == 16
     cpu = d["cpu_baseline"]
+    assert "all 32 limbs" in cpu["sample"]
     assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["sample"]
     assert cpu["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "NTT/s",
@@ -85,3 +88,43 @@ def test_clock_sampler_falls_back_to_the_nearest_samples():
     assert "shorter than one sampling period" in got["note"]
     none = bench.ClockSampler(0).stop(0.0, 1.0)
     assert none["sm_mhz"] is None and none["note"] == "nvidia-smi unavailable"
+
+
+def test_workload_config_is_the_same_object_for_both_arms():
+    """`config` names BASELINE configs[2] and nothing run-specific; at N > 1
+    it is the limb-sharded fixed-total partition (strong scaling)"""
+    one, eight = bench.workload_config(1), bench.workload_config(8)
+    assert one["ntts_per_step"] == eight["ntts_per_step"] == 1024
+    assert "limb-sharded 32/8" in eight["parallelism"]
+    assert "4 limbs" in eight["parallelism"]
+    assert set(one) == set(eight)
+
+
+def test_issue_roofline_arithmetic():
+    """slots per butterfly and the multiplier bound follow from the probe's
+    instruction rates; the register-only rate is the probe's butterfly rate"""
+    peaks = {"sm_count": 148.0, "sm_clock_mhz": 1965.0, "imad": 64.0,
+             "imad_wide": 32.0, "imad_hi": 16.0, "lop3": 64.0,
+             "bfly_forward": 4.0, "bfly_inverse": 3.0}
+    r = bench.issue_roofline(peaks, 500.0, 1900.0)
+    assert r["slots_per_butterfly"] == 4 * 2 + 4 + 4
+    bound = 64.0 / 16 * 148 * 1.9
+    assert abs(r["peak"] - bound) < 1e-9
+    assert abs(r["frac"] - 500.0 / bound) < 1e-12
+    assert abs(r["register_only_butterfly_rate"] - 3.5 * 148 * 1.9) < 1e-9
+
+
+def test_inputs_do_not_depend_on_the_sharding():
+    """a polynomial of the workload is the same data whichever rank owns it"""
+    from vkhel_b200 import params
+    primes = params.ntt_primes(bench.LIMBS)
+    saved = bench.BATCH
+    try:
+        bench.BATCH = 2
+        whole = bench.make_inputs(primes, 0, 4).reshape(2, 4, bench.N)
+        part = bench.make_inputs(primes, 2, 4).reshape(2, 2, bench.N)
+    finally:
+        bench.BATCH = saved
+    import numpy as np
+    assert np.array_equal(whole[:, 2:4], part)
+    assert (whole[0, 0] < primes[0]).all()

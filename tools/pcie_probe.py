@@ -1,60 +1,127 @@
 #!/usr/bin/env python3
-"""Host <-> device copy bandwidth through the library's own transfer calls
-(vkhel_vector_upload / vkhel_vector_download on the context's copy streams):
-each direction alone and both at once.  This is the ceiling of bench.py's
-`e2e` figure: one step moves 256 MiB in and 256 MiB out for 1024 NTTs.
+"""Host <-> device copy bandwidth WITHOUT the library: plain cudaHostAlloc /
+cudaMalloc / cudaMemcpyAsync through cuda-python, each direction alone and both
+at once, on one GPU or on N GPUs of the box at the same time.
 
-    python tools/pcie_probe.py          # prints one JSON line
+This is the ceiling of bench.py's `e2e` figure (one step moves 512 KiB in and
+512 KiB out per two NTTs): if the aggregate does not grow with the number of
+GPUs that copy concurrently, the box's host <-> device fabric is the limit and
+not the library's transfer path.
+
+    python tools/pcie_probe.py                                   # one GPU
+    python -m torch.distributed.run --nproc-per-node 8 \\
+        --master-addr 127.0.0.1 --master-port 29511 tools/pcie_probe.py
+
+Prints one JSON line on rank 0; bench.py calls measure() for its `e2e_ceiling`.
 """
 import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-
-import vkhel_b200 as vk  # noqa: E402
-
 MIB = 1 << 20
 
 
-def main():
-    ctx = vk.Context(0)
-    count = 256 * MIB // 8
-    hin, hout = vk.host_alloc(count), vk.host_alloc(count)
-    hin.array[:] = 1
-    a, b = ctx.vector(count, zero=False), ctx.vector(count, zero=False)
-    timer = ctx.timer()
-    reps = 8
+def _check(res):
+    err, rest = res[0], res[1:]
+    if int(err) != 0:
+        raise RuntimeError("CUDA runtime error %s" % err)
+    return rest[0] if len(rest) == 1 else rest
 
-    def timed(fn):
-        fn()
-        ctx.sync()
-        timer.start()
+
+def measure(device, mib=256, reps=6, barrier=None, write_combined=False):
+    """GB/s of pinned-host <-> device copies on `device`: h2d alone, d2h alone,
+    both at once (per direction).  `barrier()` (optional) is called right before
+    each timed region so that several ranks copy concurrently."""
+    from cuda.bindings import runtime as rt
+    _check(rt.cudaSetDevice(device))
+    nbytes = mib * MIB
+    up_flags = rt.cudaHostAllocWriteCombined if write_combined \
+        else rt.cudaHostAllocDefault
+    hin = _check(rt.cudaHostAlloc(nbytes, up_flags))
+    hout = _check(rt.cudaHostAlloc(nbytes, rt.cudaHostAllocDefault))
+    da = _check(rt.cudaMalloc(nbytes))
+    db = _check(rt.cudaMalloc(nbytes))
+    s_up = _check(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+    s_down = _check(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+    e0, e1, ej = (_check(rt.cudaEventCreate()) for _ in range(3))
+    h2d = rt.cudaMemcpyKind.cudaMemcpyHostToDevice
+    d2h = rt.cudaMemcpyKind.cudaMemcpyDeviceToHost
+    _check(rt.cudaMemsetAsync(da, 1, nbytes, s_up))
+    _check(rt.cudaMemsetAsync(db, 2, nbytes, s_up))
+    _check(rt.cudaStreamSynchronize(s_up))
+
+    def once(up, down):
+        if up:
+            _check(rt.cudaMemcpyAsync(da, hin, nbytes, h2d, s_up))
+        if down:
+            _check(rt.cudaMemcpyAsync(hout, db, nbytes, d2h, s_down))
+
+    def timed(up, down):
+        once(up, down)
+        _check(rt.cudaDeviceSynchronize())
+        if barrier is not None:
+            barrier()
+        # both streams start behind e0; e1 follows the end of both
+        _check(rt.cudaEventRecord(e0, s_up))
+        _check(rt.cudaStreamWaitEvent(s_down, e0, 0))
         for _ in range(reps):
-            fn()
-        timer.stop()
-        return timer.elapsed_ms() / reps
+            once(up, down)
+        _check(rt.cudaEventRecord(ej, s_down))
+        _check(rt.cudaStreamWaitEvent(s_up, ej, 0))
+        _check(rt.cudaEventRecord(e1, s_up))
+        _check(rt.cudaEventSynchronize(e1))
+        ms = _check(rt.cudaEventElapsedTime(e0, e1))
+        return nbytes * reps / (ms * 1e-3) / 1e9
 
-    ms_up = timed(lambda: a.upload(hin))
-    ms_down = timed(lambda: b.download(hout))
+    out = {
+        "device": device, "mib_per_copy": mib, "reps": reps,
+        "h2d_alone_GBps": timed(True, False),
+        "d2h_alone_GBps": timed(False, True),
+        "both_each_GBps": timed(True, True),
+        "write_combined_upload_buffer": bool(write_combined),
+    }
+    for ev in (e0, e1, ej):
+        _check(rt.cudaEventDestroy(ev))
+    _check(rt.cudaStreamDestroy(s_up))
+    _check(rt.cudaStreamDestroy(s_down))
+    _check(rt.cudaFree(da))
+    _check(rt.cudaFree(db))
+    _check(rt.cudaFreeHost(hin))
+    _check(rt.cudaFreeHost(hout))
+    return out
 
-    def both():
-        a.upload(hin)
-        b.download(hout)
 
-    ms_both = timed(both)
-    gb = count * 8 / 1e9
-    print(json.dumps({
-        "bytes_per_copy": count * 8,
-        "h2d_alone_GBps": gb / (ms_up * 1e-3),
-        "d2h_alone_GBps": gb / (ms_down * 1e-3),
-        "both_each_GBps": gb / (ms_both * 1e-3),
-        "e2e_ceiling_ntt_per_s": 1024 / (ms_both * 1e-3),
-    }))
-    timer.destroy()
-    a.destroy(), b.destroy()
-    hin.free(), hout.free()
-    ctx.destroy()
+def summarise(per_rank):
+    """aggregate over the ranks that copied concurrently; the e2e ceiling in
+    NTT/s at n = 2^16: 512 KiB in and 512 KiB out per NTT pair, i.e. 256 KiB
+    each way per NTT while both directions are active"""
+    total = {k: sum(r[k] for r in per_rank)
+             for k in ("h2d_alone_GBps", "d2h_alone_GBps", "both_each_GBps")}
+    total["n_gpus"] = len(per_rank)
+    total["e2e_ceiling_ntt_per_s"] = total["both_each_GBps"] * 1e9 / (256 * 1024)
+    return total
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wc = "--write-combined" in sys.argv
+    barrier, dist = None, None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        barrier = dist.barrier
+    mine = measure(local_rank, barrier=barrier, write_combined=wc)
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        dist.destroy_process_group()
+    else:
+        gathered = [mine]
+    if rank == 0:
+        print(json.dumps({"aggregate": summarise(gathered),
+                          "per_rank": gathered}))
 
 
 if __name__ == "__main__":

@@ -84,6 +84,9 @@ SIGNATURES = {
     "vkhel_ntt_tables_create_on": (_vp, [_vp, _u64, _u64, _u64]),
     "vkhel_ctx_deferred_stats": (None, [_vp, _p64, _p64]),
     "vkhel_ctx_fused_products": (ctypes.c_uint64, [_vp]),
+    "vkhel_ctx_probe_int_peaks": (ctypes.c_int, [_vp,
+                                                 ctypes.POINTER(ctypes.c_double),
+                                                 ctypes.c_int]),
 }
 
 _lib = None
@@ -270,6 +273,17 @@ class Context:
 
     def flush_l2(self):
         lib().vkhel_ctx_flush_l2(self.handle)
+
+    def probe_int_peaks(self):
+        """integer-pipe rates of this context's device, measured now
+        (vkhel_ctx_probe_int_peaks): thread-instructions, respectively
+        butterflies, per clock per SM"""
+        buf = (ctypes.c_double * 12)()
+        n = lib().vkhel_ctx_probe_int_peaks(self.handle, buf, 12)
+        names = ["sm_count", "sm_clock_mhz", "imad", "imad_wide", "imad_hi",
+                 "lop3", "bfly_forward", "bfly_inverse", "shf", "iadd3",
+                 "add64_3in", "csub64"]
+        return {k: float(buf[i]) for i, k in enumerate(names[:n])}
 
     def flush(self):
         """launch the recorded single-vector transforms (no wait)"""

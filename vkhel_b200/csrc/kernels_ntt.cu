@@ -27,6 +27,9 @@
  * ntt_engine.cuh), the single-pass, row-only and generic kernels fold it into
  * their last stage (twiddles n^-1 and inv_root[1] * n^-1, FOLD_LAST).
  */
+#include <string.h>
+#include <type_traits>
+
 #include "common.cuh"
 #include "ntt_engine.cuh"
 
@@ -300,6 +303,34 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 #ifndef FAST_PDL_EARLY
 #define FAST_PDL_EARLY 0
 #endif
+/* three-input additions with a zero only the host knows keep the butterflies'
+ * additions off the fmaheavy pipe (modarith.cuh, ct_lazy); 0 = plain sums */
+#ifndef FAST_OPAQUE_ZERO
+#define FAST_OPAQUE_ZERO 0
+#endif
+/* Stores of two adjacent 64-bit values as two 64-bit stores instead of one
+ * 128-bit store: a 128-bit store wants its four source registers in one
+ * aligned quad, and ptxas assembles that quad with up to three register moves
+ * per store (58-169 IMAD.MOV per column kernel, on the fmaheavy pipe); a pair
+ * of 64-bit stores takes the values where the butterflies left them.
+ * XST: shared-memory exchange stores, GST: global stores. */
+#ifndef COLS_XST64
+#define COLS_XST64 0
+#endif
+#ifndef COLS_GST64
+#define COLS_GST64 0
+#endif
+#ifndef ROWS_XST64
+#define ROWS_XST64 0
+#endif
+#ifndef ROWS_GST64
+#define ROWS_GST64 0
+#endif
+#if FAST_OPAQUE_ZERO
+#define OPAQUE_ZERO(p) ((p).zero)
+#else
+#define OPAQUE_ZERO(p) ((u64) 0)
+#endif
 
 struct fast_pass {
 	const u64 *src;
@@ -325,6 +356,9 @@ struct fast_pass {
 	 * laid out [batch][limbs_total][n]; descs already points at limb0.  The
 	 * whole vector: limb0 = 0, limbs_total = limbs. */
 	unsigned limbs_total, limb0;
+	/* always 0, but only the host knows: three-input additions with it stay
+	 * on the ALU pipe (modarith.cuh, ct_lazy) */
+	u64 zero;
 
 	__host__ __device__ bool indirect() const {
 		return tab != NULL || tab_inline != 0;
@@ -358,6 +392,23 @@ __host__ __device__ constexpr int xpad(int i) {
 #else
 	return i + ((i >> 5) << 2);
 #endif
+}
+
+/* 64-bit shared-memory store at a compile-time offset from a per-thread base,
+ * as inline PTX so that the compiler's store vectoriser cannot merge two of
+ * them back into one 128-bit store (see COLS_XST64) */
+template <int OFF_BYTES>
+__device__ __forceinline__ void sts64_at(unsigned base, u64 v) {
+	asm volatile("st.shared.b64 [%0+%1], %2;"
+			:: "r"(base), "n"(OFF_BYTES), "l"(v) : "memory");
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+	if constexpr (I < N) {
+		f(std::integral_constant<int, I>());
+		static_for<I + 1, N>(f);
+	}
 }
 
 /* ---- programmatic dependent launch (PDL) ------------------------------------------
@@ -409,6 +460,17 @@ static void launch_fast(struct vkhel_ctx *ctx, void (*kernel)(KArgs...),
 	cfg.numAttrs = 1;
 	CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
 	ctx->dev.launches++;
+}
+
+/* launch_fast with the shared-memory opt-in where the kernel needs it (per
+ * device, and cheap: set on every such launch) */
+static void launch_fast_optin(struct vkhel_ctx *ctx, void (*kernel)(fast_pass),
+		unsigned grid, unsigned block, size_t smem, const fast_pass &p) {
+	if (smem_needs_optin(smem)) {
+		CUDA_CHECK(cudaFuncSetAttribute(kernel,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	}
+	launch_fast(ctx, kernel, grid, block, smem, p);
 }
 
 /* ---- twiddle staging by TMA bulk copies --------------------------------------------
@@ -481,10 +543,15 @@ struct row_cfg {
 /* Row pass.  CTA = (batch chunk, limb, H group): `bchunk` batch entries of
  * 2^hgroup_log2 consecutive tiles sharing one staged twiddle set.  A warp-group
  * of 2^(K-3) lanes carries NP batch entries of one tile position at a time. */
-template <bool INV, int K, int NP, bool MUL, bool APX, bool IND>
+/* TOP (inverse only): the pass holds stage 0 (s0 == 0, i.e. the row pass is the
+ * whole transform) and applies n^-1 in it.  A template parameter rather than
+ * a run-time branch per round: with both variants in one kernel ptxas merged
+ * their register assignments after every round with some 20 moves each. */
+template <bool INV, int K, int NP, bool MUL, bool APX, bool IND, bool TOP>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const __grid_constant__ fast_pass p) {
+	static_assert(INV || !TOP, "TOP distinguishes inverse passes only");
 	static_assert(!(IND && MUL), "no indirect fused product");
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
@@ -530,8 +597,8 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 	u64 *xb = sm_x + (size_t) slot * (NP * C::xbuf);
 	constexpr int first = INV ? G::rounds - 1 : 0;
 	constexpr int last = INV ? 0 : G::rounds - 1;
-	const bool fold = INV && s0 == 0;
-	const bool canon = INV ? s0 == 0 : true;     /* pass with the final stage */
+	constexpr bool fold = INV && TOP;
+	constexpr bool canon = INV ? TOP : true;     /* pass with the final stage */
 	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
 	if (fold) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
@@ -633,12 +700,12 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 			mbar_wait(&tw_bar, 0);   /* twiddles have landed */
 			tw_ready = true;
 		}
-#pragma unroll
-		for (int rr = 0; rr < G::rounds; rr++) {
-			const int r = INV ? G::rounds - 1 - rr : rr;
-			if (rr > 0) {
+		static_for<0, G::rounds>([&](auto rrc) {
+			constexpr int rr = decltype(rrc)::value;
+			constexpr int r = INV ? G::rounds - 1 - rr : rr;
+			if constexpr (rr > 0) {
 				/* redistribute: previous round's layout -> this round's */
-				const int prev = INV ? r + 1 : r - 1;
+				constexpr int prev = INV ? r + 1 : r - 1;
 				/* where registers (e, e+1) are adjacent coefficients (the
 				 * deepest round) the exchange moves 128 bits at a time: half
 				 * the shared-memory instructions and half the bank conflicts
@@ -646,7 +713,15 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 				u64 *xw = xb + xpad(G::tbase(prev, t));
 #pragma unroll
 				for (int pp = 0; pp < NP; pp++) {
-					if (G::eoff(prev, 1) == 1) {
+					if (ROWS_XST64) {
+						const unsigned xa =
+							(unsigned) __cvta_generic_to_shared(xw + pp * C::xbuf)
+							+ (unsigned) OPAQUE_ZERO(p);
+						static_for<0, 8>([&](auto ec) {
+							constexpr int e = decltype(ec)::value;
+							sts64_at<8 * xpad(G::eoff(prev, e))>(xa, x[pp][e]);
+						});
+					} else if (G::eoff(prev, 1) == 1) {
 #pragma unroll
 						for (int e = 0; e < 8; e += 2) {
 							*(ulonglong2 *) (xw + pp * C::xbuf
@@ -680,14 +755,9 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 					}
 				}
 			}
-			if (fold) {
-				tile_round<K, INV, INV ? FOLD_LAST : FOLD_NONE, NP, APX>(x, r, t,
-						twt, q, bq, fold_a, fold_b);
-			} else {
-				tile_round<K, INV, FOLD_NONE, NP, APX>(x, r, t, twt, q, bq,
-						fold_a, fold_b);
-			}
-		}
+			tile_round<K, INV, fold ? FOLD_LAST : FOLD_NONE, NP, APX>(x, r, t,
+					twt, q, bq, fold_a, fold_b, nullptr, OPAQUE_ZERO(p));
+		});
 		__syncwarp();   /* the exchange buffer is reused by the next item */
 		if (base + C::groups_per_cta >= nitems) {
 			pdl_launch_dependents();   /* only this CTA's last stores remain */
@@ -703,7 +773,7 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 						x[pp][e] = tile_canon<INV, APX>(x[pp][e], q, bq);
 					}
 				}
-				if (G::eoff(last, 1) == 1) {
+				if (G::eoff(last, 1) == 1 && !ROWS_GST64) {
 					/* adjacent coefficients in (e, e+1): 128-bit stores */
 #pragma unroll
 					for (int e = 0; e < 8; e += 2) {
@@ -734,7 +804,7 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 template <bool INV, int K, bool FOLD, bool APX>
 __device__ __forceinline__ void rows_rounds(u64 (&x)[1][8], u64 *xb, int t,
 		const ulonglong2 *twt, u64 q, u64 bq, ulonglong2 fold_a,
-		ulonglong2 fold_b) {
+		ulonglong2 fold_b, u64 zr) {
 	using G = tile_geom<K>;
 #pragma unroll
 	for (int rr = 0; rr < G::rounds; rr++) {
@@ -772,7 +842,7 @@ __device__ __forceinline__ void rows_rounds(u64 (&x)[1][8], u64 *xb, int t,
 			}
 		}
 		tile_round<K, INV, FOLD ? FOLD_LAST : FOLD_NONE, 1, APX>(x, r, t, twt, q,
-				bq, fold_a, fold_b);
+				bq, fold_a, fold_b, nullptr, zr);
 	}
 }
 
@@ -862,9 +932,11 @@ ntt_rows_polymul_kernel(const __grid_constant__ fast_pass p) {
 			mbar_wait(&tw_bar[1], 0);
 			tw_ready = true;
 		}
-		rows_rounds<false, K, false, APX>(xa, xb, t, twf, q, bq, fold_a, fold_b);
+		rows_rounds<false, K, false, APX>(xa, xb, t, twf, q, bq, fold_a, fold_b,
+				OPAQUE_ZERO(p));
 		__syncwarp();   /* the exchange buffer changes hands */
-		rows_rounds<false, K, false, APX>(x, xb, t, twf, q, bq, fold_a, fold_b);
+		rows_rounds<false, K, false, APX>(x, xb, t, twf, q, bq, fold_a, fold_b,
+				OPAQUE_ZERO(p));
 		/* point-wise product (reference elemmul.comp:62-73): one factor is
 		 * made canonical, the other stays lazy (below 2*bq), so the high word
 		 * of the product is below q as reduce128 requires; the result is the
@@ -875,9 +947,11 @@ ntt_rows_polymul_kernel(const __grid_constant__ fast_pass p) {
 			x[0][e] = mulmod(ca, x[0][e], m);
 		}
 		if (fold) {
-			rows_rounds<true, K, true, APX>(x, xb, t, twi, q, bq, fold_a, fold_b);
+			rows_rounds<true, K, true, APX>(x, xb, t, twi, q, bq, fold_a, fold_b,
+					OPAQUE_ZERO(p));
 		} else {
-			rows_rounds<true, K, false, APX>(x, xb, t, twi, q, bq, fold_a, fold_b);
+			rows_rounds<true, K, false, APX>(x, xb, t, twi, q, bq, fold_a, fold_b,
+					OPAQUE_ZERO(p));
 		}
 		__syncwarp();   /* the exchange buffer is reused by the next item */
 		if (base + C::groups_per_cta >= nitems) {
@@ -1042,7 +1116,7 @@ ntt_single_kernel(const __grid_constant__ fast_pass p) {
 				 * just read: no second barrier */
 			}
 			tile_round<K, INV, INV ? FOLD_LAST : FOLD_NONE, 1, APX>(x, r, t,
-					sm_tw, q, bq, fold_a, fold_b);
+					sm_tw, q, bq, fold_a, fold_b, nullptr, OPAQUE_ZERO(p));
 		}
 		if (bl + 1 == nb) {
 			pdl_launch_dependents();   /* only this CTA's last stores remain */
@@ -1092,7 +1166,11 @@ template <int NP> struct col_vec;
 template <> struct col_vec<1> { typedef u64 type; };
 template <> struct col_vec<2> { typedef ulonglong2 type; };
 
-template <bool INV, int K, int CL, int NP, bool APX, bool IND>
+/* (Tried: the row stride as a template parameter, so that every global access
+ * is "per-thread base + immediate" -- 80 instructions fewer per thread, and the
+ * forward pass 7 % SLOWER, 156.4 against 146.0 us, inverse unchanged:
+ * profiles/r02_kernel_ab.txt, variant n0 against the LB8 build.) */
+template <bool INV, int K, int CL, int NP, bool APX, bool IND, bool TOP>
 __global__ void __launch_bounds__(1 << (K - 3 + CL - (NP == 2 ? 1 : 0)),
 		((NP == 2 ? COLS_MIN_THREADS_NP2 : COLS_MIN_THREADS_NP1)
 			>> (K - 3 + CL - (NP == 2 ? 1 : 0))) > 0
@@ -1142,13 +1220,14 @@ ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 	 * when this pass holds stage 0.  (A one-CTA-per-polynomial single-launch
 	 * variant of this kernel, K = log2 n, was measured no faster than the
 	 * two-pass split even for a single polynomial.) */
-	const bool fold = INV && s0 == 0;
-	constexpr int FM = INV ? COLS_FOLD : FOLD_NONE;
+	static_assert(INV || !TOP, "TOP distinguishes inverse passes only");
+	constexpr bool fold = INV && TOP;            /* TOP: s0 == 0 */
+	constexpr int FM = fold ? COLS_FOLD : FOLD_NONE;
 	static_assert(K <= SCALED_TW_MAX_LOG2, "scaled twiddles cover 2^10 nodes");
 	/* FOLD_TWID: the tile is the top of the heap (root 1); its scaled copy
 	 * lies behind the coefficients' exchange buffer */
 	const ulonglong2 *sm_tws = (const ulonglong2 *) (sm_x + ((size_t) 1 << (K + CL)));
-	const bool scaled_tw = FM == FOLD_TWID && fold;
+	constexpr bool scaled_tw = FM == FOLD_TWID && fold;
 
 	__shared__ __align__(8) u64 tw_bar;
 	if (threadIdx.x == 0) {
@@ -1181,7 +1260,7 @@ ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 			}
 		}
 	}
-	const bool canon = fold;
+	constexpr bool canon = fold;
 	ulonglong2 fold_a = make_ulonglong2(0, 0), fold_b = fold_a;
 	if (fold) {
 		fold_a = make_ulonglong2(d.inv_n, d.inv_n_shoup);
@@ -1189,20 +1268,36 @@ ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 	}
 	mbar_wait(&tw_bar, 0);   /* twiddles have landed */
 
-#pragma unroll
-	for (int rr = 0; rr < G::rounds; rr++) {
-		const int r = INV ? G::rounds - 1 - rr : rr;
-		if (rr > 0) {
-			const int prev = INV ? r + 1 : r - 1;
+	static_for<0, G::rounds>([&](auto rrc) {
+		constexpr int rr = decltype(rrc)::value;
+		constexpr int r = INV ? G::rounds - 1 - rr : rr;
+		if constexpr (rr > 0) {
+			constexpr int prev = INV ? r + 1 : r - 1;
 			u64 *xw = sm_x + (G::tbase(prev, t) << CL) + c;
 #pragma unroll
 			for (int e = 0; e < 8; e++) {
+				if (COLS_XST64) {
+					break;
+				}
 				vec_t v;
 				((u64 *) &v)[0] = x[0][e];
 				if (NP == 2) {
 					((u64 *) &v)[NP - 1] = x[NP - 1][e];
 				}
 				*(vec_t *) (xw + (G::eoff(prev, e) << CL)) = v;
+			}
+			if (COLS_XST64) {
+				/* (the opaque zero hides the base's 16-byte alignment from
+				 * ptxas, which would otherwise fuse the pairs again) */
+				const unsigned xa = (unsigned) __cvta_generic_to_shared(xw)
+					+ (unsigned) OPAQUE_ZERO(p);
+				static_for<0, 8>([&](auto ec) {
+					constexpr int e = decltype(ec)::value;
+					static_for<0, NP>([&](auto pc) {
+						constexpr int pp = decltype(pc)::value;
+						sts64_at<8 * ((G::eoff(prev, e) << CL) + pp)>(xa, x[pp][e]);
+					});
+				});
 			}
 			__syncthreads();
 			const u64 *xr = sm_x + (G::tbase(r, t) << CL) + c;
@@ -1215,14 +1310,9 @@ ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 				}
 			}
 		}
-		if (fold) {
-			tile_round<K, INV, FM, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b,
-					sm_tws);
-		} else {
-			tile_round<K, INV, FOLD_NONE, NP, APX>(x, r, t, sm_tw, q, bq, fold_a,
-					fold_b);
-		}
-	}
+		tile_round<K, INV, FM, NP, APX>(x, r, t, sm_tw, q, bq, fold_a, fold_b,
+				sm_tws, OPAQUE_ZERO(p));
+	});
 
 	pdl_launch_dependents();   /* only this CTA's stores remain */
 	u64 *dp = dst_base + base + ((u64) G::tbase(last, t) << low_bits);
@@ -1233,11 +1323,26 @@ ntt_cols_kernel(const __grid_constant__ fast_pass p) {
 		for (int pp = 0; pp < NP; pp++) {
 			u64 w = x[pp][e];
 			if (canon) {
-				w = tile_canon<true, APX, FM == FOLD_NONE ? FOLD_LAST : FM>(w, q, bq);
+				w = tile_canon<true, APX, FM>(w, q, bq);
+			}
+			if (COLS_GST64) {
+				dp[((u64) G::eoff(last, e) << low_bits) + pp] = w;
 			}
 			((u64 *) &v)[pp] = w;
 		}
-		*(vec_t *) (dp + ((u64) G::eoff(last, e) << low_bits)) = v;
+		if (!COLS_GST64) {
+			*(vec_t *) (dp + ((u64) G::eoff(last, e) << low_bits)) = v;
+		}
+	}
+	if (FM == FOLD_TWID && scaled_tw && t == 0) {
+		/* coefficient 0 of the tile (register 0 of row group 0) is the one
+		 * value no difference has scaled (ntt_engine.cuh): the explicit
+		 * product, stored over what this thread has just written there */
+#pragma unroll
+		for (int pp = 0; pp < NP; pp++) {
+			const u64 w = shoup_lazy(x[pp][0], fold_a.x, fold_a.y, q);
+			dp[pp] = csub(w, q);
+		}
 	}
 }
 
@@ -1269,27 +1374,29 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	VK_REQUIRE(blocks <= 0x7fffffffull, "transform too large for one launch");
 	const size_t smem = ((size_t) sizeof(ulonglong2) << (hgroup_log2 + K))
 		+ (size_t) C::groups_per_cta * NP * C::xbuf * sizeof(u64);
+	/* inverse: the variant that holds stage 0 (and n^-1), or the plain one */
+	const bool top = INV && p.s0 == 0;
+	void (*kernel)(fast_pass);
 	if constexpr (!MUL) {
 		if (p.indirect()) {
-			if (smem_needs_optin(smem)) {
-				CUDA_CHECK(cudaFuncSetAttribute(
-							ntt_rows_kernel<INV, K, NP, false, APX, true>,
-							cudaFuncAttributeMaxDynamicSharedMemorySize,
-							(int) smem));
+			if constexpr (INV) {
+				kernel = top ? ntt_rows_kernel<INV, K, NP, false, APX, true, true>
+					: ntt_rows_kernel<INV, K, NP, false, APX, true, false>;
+			} else {
+				kernel = ntt_rows_kernel<INV, K, NP, false, APX, true, false>;
 			}
-			launch_fast(ctx, ntt_rows_kernel<INV, K, NP, false, APX, true>,
-					(unsigned) blocks, FAST_THREADS, smem, p);
+			launch_fast_optin(ctx, kernel, (unsigned) blocks, FAST_THREADS,
+					smem, p);
 			return;
 		}
 	}
-	if (smem_needs_optin(smem)) {
-		/* per device, and cheap: set it on every such launch */
-		CUDA_CHECK(cudaFuncSetAttribute(
-					ntt_rows_kernel<INV, K, NP, MUL, APX, false>,
-					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	if constexpr (INV) {
+		kernel = top ? ntt_rows_kernel<INV, K, NP, MUL, APX, false, true>
+			: ntt_rows_kernel<INV, K, NP, MUL, APX, false, false>;
+	} else {
+		kernel = ntt_rows_kernel<INV, K, NP, MUL, APX, false, false>;
 	}
-	launch_fast(ctx, ntt_rows_kernel<INV, K, NP, MUL, APX, false>,
-			(unsigned) blocks, FAST_THREADS, smem, p);
+	launch_fast_optin(ctx, kernel, (unsigned) blocks, FAST_THREADS, smem, p);
 }
 
 template <bool INV, int K, bool APX>
@@ -1323,33 +1430,43 @@ static void run_cols_cl(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const size_t smem = (sizeof(ulonglong2) << K) + (sizeof(u64) << (K + CL))
 		+ (INV && COLS_FOLD == FOLD_TWID && p.s0 == 0
 				? sizeof(ulonglong2) << K : 0);
+	const bool top = INV && p.s0 == 0;
+	void (*kernel)(fast_pass);
 	if (p.indirect()) {
-		if (smem_needs_optin(smem)) {
-			CUDA_CHECK(cudaFuncSetAttribute(
-						ntt_cols_kernel<INV, K, CL, NP, APX, true>,
-						cudaFuncAttributeMaxDynamicSharedMemorySize,
-						(int) smem));
+		if constexpr (INV) {
+			kernel = top ? ntt_cols_kernel<INV, K, CL, NP, APX, true, true>
+				: ntt_cols_kernel<INV, K, CL, NP, APX, true, false>;
+		} else {
+			kernel = ntt_cols_kernel<INV, K, CL, NP, APX, true, false>;
 		}
-		launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX, true>,
-				(unsigned) blocks, C::threads, smem, p);
-		return;
+	} else {
+		if constexpr (INV) {
+			kernel = top ? ntt_cols_kernel<INV, K, CL, NP, APX, false, true>
+				: ntt_cols_kernel<INV, K, CL, NP, APX, false, false>;
+		} else {
+			kernel = ntt_cols_kernel<INV, K, CL, NP, APX, false, false>;
+		}
 	}
-	if (smem_needs_optin(smem)) {
-		CUDA_CHECK(cudaFuncSetAttribute(
-					ntt_cols_kernel<INV, K, CL, NP, APX, false>,
-					cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	}
-	launch_fast(ctx, ntt_cols_kernel<INV, K, CL, NP, APX, false>,
-			(unsigned) blocks, C::threads, smem, p);
+	launch_fast_optin(ctx, kernel, (unsigned) blocks, C::threads, smem, p);
 }
 
 /* 256 threads per CTA: 2^(12-K) columns with two columns per thread, 2^(11-K)
  * with one; the 8-point column pass of n = 2^9 and 2^10 has only 64 / 128
  * columns to offer and runs with fewer threads */
+#ifndef COLS_THREADS_LOG2
+#define COLS_THREADS_LOG2 8
+#endif
 template <bool INV, int K, bool APX>
 static void run_cols(struct vkhel_ctx *ctx, const fast_pass &p) {
 	const unsigned low_bits = p.log2n - p.s0 - K;
 	if constexpr (COLS_NP == 2 && K <= 8) {
+		/* CTA of 2^COLS_THREADS_LOG2 threads: 2^(K-3) row groups by
+		 * 2^(COLS_THREADS_LOG2 + 4 - K) columns, two per thread */
+		constexpr int CLW = COLS_THREADS_LOG2 + 4 - K;
+		if (CLW >= 1 && low_bits >= (unsigned) CLW) {
+			run_cols_cl<INV, K, CLW < 1 ? 1 : CLW, 2, APX>(ctx, p);
+			return;
+		}
 		if (low_bits >= 12 - K) {
 			run_cols_cl<INV, K, 12 - K, 2, APX>(ctx, p);
 			return;
@@ -1547,6 +1664,18 @@ static fast_plan plan_fast(unsigned log2n, bool forward_only = false) {
 	return pl;
 }
 
+/* $VKHEL_ONLY_PASS=cols|rows launches only that pass of a two-pass transform:
+ * results are INVALID, the switch exists to time the passes apart
+ * (tools/kernel_ab.py) */
+static int only_pass() {
+	static int v = -1;
+	if (v < 0) {
+		const char *env = getenv("VKHEL_ONLY_PASS");
+		v = !env ? 0 : !strcmp(env, "cols") ? 1 : !strcmp(env, "rows") ? 2 : 0;
+	}
+	return v;
+}
+
 template <bool INV, bool APX>
 static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
@@ -1555,6 +1684,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const ntt_ptrs *inline_tab = NULL) {
 	const fast_plan pl = plan_fast(log2n, !INV);
 	fast_pass p;
+	p.zero = 0;
 	p.tab = tab;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -1603,7 +1733,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 			run_generic_pass<false, false>(ctx, lead);
 			cur = dst;
 		}
-		if (pl.kcol) {
+		if (pl.kcol && only_pass() != 2) {
 			p.src = cur;
 			p.dst = dst;
 			p.s0 = pl.lead;
@@ -1614,16 +1744,20 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		p.src = cur;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
-		run_rows_k<false, APX>(ctx, p, pl.krow);
+		if (!pl.kcol || only_pass() != 1) {
+			run_rows_k<false, APX>(ctx, p, pl.krow);
+		}
 	} else {
 		p.src = src;
 		p.src2 = src2;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
-		run_rows_k<true, APX>(ctx, p, pl.krow);
+		if (!pl.kcol || only_pass() != 1) {
+			run_rows_k<true, APX>(ctx, p, pl.krow);
+		}
 		p.src2 = NULL;
 		p.tab_second = 1;
-		if (pl.kcol) {
+		if (pl.kcol && only_pass() != 2) {
 			p.src = dst;
 			p.s0 = pl.lead;
 			run_cols_k<true, APX>(ctx, p, pl.kcol);
@@ -1693,6 +1827,7 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 		uint64_t polys, unsigned log2n) {
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
+	p.zero = 0;
 	p.tab = NULL;
 	p.tab_second = 0;
 	p.tab_inline = 0;

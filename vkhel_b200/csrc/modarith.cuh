@@ -44,8 +44,12 @@ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) {
  * so that ptxas emits the ten (nine) multiplies as IMAD / IMAD.WIDE / IMAD.HI
  * with their accumulators chained and no separate add, negate or move
  * (tools/bfly_bench.cu v19: +7 % butterfly rate over the C expression). */
+#ifndef SHOUP_SPARSE60
+#define SHOUP_SPARSE60 0
+#endif
 template <bool APPROX>
-__device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq) {
+__device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq,
+		unsigned zr = 0) {
 	const unsigned y0 = (unsigned) y, y1 = (unsigned) (y >> 32);
 	const unsigned w0 = (unsigned) w, w1 = (unsigned) (w >> 32);
 	const unsigned p0 = (unsigned) wp, p1 = (unsigned) (wp >> 32);
@@ -67,12 +71,20 @@ __device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq) {
 		    "madc.hi.u32 %1, h0, %8, %1;\n\t"
 		    "mad.lo.u32 %1, %2, %5, %1;\n\t"       /* t.hi += y0*w1 */
 		    "mad.lo.u32 %1, %3, %4, %1;\n\t"       /* t.hi += y1*w0 */
+#if SHOUP_SPARSE60
+		    /* experiment, moduli in (2^60 - 2^32, 2^60) only: the high word
+		     * of 2^64 - q is 0xF0000000, so h0*n1 = -(h0 << 28) mod 2^32 */
+		    "shf.l.clamp.b32 r0, 0, h0, 28;\n\t"
+		    "sub.u32 %1, %1, r0;\n\t"
+		    "add.u32 %1, %1, %10;\n\t"
+#else
 		    "mad.lo.u32 %1, h0, %9, %1;\n\t"       /* t.hi += h0*n1 */
+#endif
 		    "mad.lo.u32 %1, h1, %8, %1;\n\t"       /* t.hi += h1*n0 */
 		    "}"
 		    : "=&r"(t0), "=&r"(t1)
 		    : "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0),
-		      "r"(n1));
+		      "r"(n1), "r"(zr));
 	} else {
 		asm("{\n\t"
 		    ".reg .u32 r0, h0, h1;\n\t"
@@ -135,8 +147,9 @@ __device__ __forceinline__ u64 mulhi64_approx(u64 a, u64 b) {
 /* Shoup product with the approximate quotient: the quotient estimate is at
  * most one further below the true one, so the result is y*w mod q plus
  * {0, q, 2q}: in [0,3q) for ANY 64-bit y.  Needs 3q < 2^64. */
-__device__ __forceinline__ u64 shoup_lazy3(u64 y, u64 w, u64 wp, u64 q) {
-	return shoup_chain<true>(y, w, wp, 0 - q);
+__device__ __forceinline__ u64 shoup_lazy3(u64 y, u64 w, u64 wp, u64 q,
+		unsigned zr = 0) {
+	return shoup_chain<true>(y, w, wp, 0 - q, zr);
 }
 
 __device__ __forceinline__ u64 shoup_canon(u64 y, u64 w, u64 wp, u64 q) {
@@ -168,17 +181,24 @@ __device__ __forceinline__ u64 csub(u64 x, u64 m) {
  * inverse (Gentleman-Sande, reference nttrevbutterfly.comp:41-57):
  *   in : x, y in [0,2q)      out: x' = x + y, y' = (x - y)*w, both in [0,2q)
  */
+/* `zr` is a zero the compiler cannot see through (a kernel parameter).  The
+ * two-input sums x' = xr + t and s = x + y are written as three-input sums with
+ * it: ptxas then keeps both words of the addition on the ALU pipe (IADD3 /
+ * IADD3.X with three addends), where it otherwise moves the high word of about
+ * two in three such additions to IMAD.X "to balance the pipes" -- 1.1 issue
+ * slots each on the fmaheavy pipe, the one that binds these kernels
+ * (profiles/r02_sass_census.txt). */
 __device__ __forceinline__ void ct_lazy(u64 &x, u64 &y, u64 w, u64 wp,
-		u64 q, u64 twoq) {
+		u64 q, u64 twoq, u64 zr = 0) {
 	const u64 xr = csub(x, twoq);
 	const u64 t = shoup_lazy(y, w, wp, q);
-	x = xr + t;
+	x = xr + t + zr;
 	y = xr - t + twoq;
 }
 
 __device__ __forceinline__ void gs_lazy(u64 &x, u64 &y, u64 w, u64 wp,
-		u64 q, u64 twoq) {
-	const u64 s = x + y;
+		u64 q, u64 twoq, u64 zr = 0) {
+	const u64 s = x + y + zr;
 	const u64 d = x - y + twoq;
 	x = csub(s, twoq);
 	y = shoup_lazy(d, w, wp, q);
@@ -188,19 +208,19 @@ __device__ __forceinline__ void gs_lazy(u64 &x, u64 &y, u64 w, u64 wp,
  * forward: x, y in [0,6q) -> [0,6q); inverse: x, y in [0,3q) -> [0,3q).
  * threeq = 3q.  One conditional subtraction per butterfly, as above. */
 __device__ __forceinline__ void ct_lazy3(u64 &x, u64 &y, u64 w, u64 wp,
-		u64 q, u64 threeq) {
+		u64 q, u64 threeq, u64 zr = 0) {
 	const u64 xr = csub(x, threeq);
-	const u64 t = shoup_lazy3(y, w, wp, q);
-	x = xr + t;
+	const u64 t = shoup_lazy3(y, w, wp, q, (unsigned) zr);
+	x = xr + t + zr;
 	y = xr - t + threeq;
 }
 
 __device__ __forceinline__ void gs_lazy3(u64 &x, u64 &y, u64 w, u64 wp,
-		u64 q, u64 threeq) {
-	const u64 s = x + y;
+		u64 q, u64 threeq, u64 zr = 0) {
+	const u64 s = x + y + zr;
 	const u64 d = x - y + threeq;
 	x = csub(s, threeq);
-	y = shoup_lazy3(d, w, wp, q);
+	y = shoup_lazy3(d, w, wp, q, (unsigned) zr);
 }
 
 /* ---- strict butterflies: every value canonical (2^62 <= q < 2^63) ---------- */

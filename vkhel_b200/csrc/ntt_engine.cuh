@@ -102,7 +102,8 @@ struct tile_geom {
  *               its sum stays unscaled.  Both inputs of a butterfly always have
  *               the same history, and scaled inputs use the plain twiddle.
  *               After the last stage exactly one coefficient of the tile
- *               (index 0) is still unscaled and gets the one explicit product.
+ *               (index 0) is still unscaled and gets the one explicit product
+ *               (by the kernel, when it stores).
  *               Which butterflies are concerned is static per register (the
  *               pair bits of this round below the current one are zero) and per
  *               thread (the bits paired in earlier rounds are zero), so the
@@ -115,11 +116,12 @@ enum { FOLD_NONE = 0, FOLD_LAST = 1, FOLD_TWID = 2 };
  *   twt: the tile's twiddle subtree in shared memory, twt[node] = (w, w')
  *   tws: FOLD_TWID only -- the same subtree of the scaled inverse table
  *   FOLD: see above; fold_a = n^-1, fold_b = inv_root[1] * n^-1
- *   APX:  butterflies around the approximate Shoup product (bq = 3q) */
+ *   APX:  butterflies around the approximate Shoup product (bq = 3q)
+ *   zr:   an opaque zero (modarith.cuh, ct_lazy) */
 template <int K, bool INV, int FOLD, int NP, bool APX>
 __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 		const ulonglong2 *twt, u64 q, u64 bq, ulonglong2 fold_a,
-		ulonglong2 fold_b, const ulonglong2 *tws = nullptr) {
+		ulonglong2 fold_b, const ulonglong2 *tws = nullptr, u64 zr = 0) {
 	using G = tile_geom<K>;
 	static_assert(INV || FOLD == FOLD_NONE, "only the inverse carries n^-1");
 	const int cnt = G::cnt(r);
@@ -168,23 +170,18 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 					u64 &X = x[p][e];
 					u64 &Y = x[p][e | (1 << beta)];
 					if (INV) {
-						if (APX) gs_lazy3(X, Y, w.x, w.y, q, bq);
-						else gs_lazy(X, Y, w.x, w.y, q, bq);
+						if (APX) gs_lazy3(X, Y, w.x, w.y, q, bq, zr);
+						else gs_lazy(X, Y, w.x, w.y, q, bq, zr);
 					} else {
-						if (APX) ct_lazy3(X, Y, w.x, w.y, q, bq);
-						else ct_lazy(X, Y, w.x, w.y, q, bq);
+						if (APX) ct_lazy3(X, Y, w.x, w.y, q, bq, zr);
+						else ct_lazy(X, Y, w.x, w.y, q, bq, zr);
 					}
 				}
-				if (INV && FOLD == FOLD_TWID && u == 0 && upos) {
-					/* the tile's coefficient 0 (register 0 of group-thread 0):
-					 * the one value no difference has scaled */
-					if (unscaled_thread) {
-#pragma unroll
-						for (int p = 0; p < NP; p++) {
-							x[p][e] = shoup_lazy(x[p][e], fold_a.x, fold_a.y, q);
-						}
-					}
-				}
+				/* FOLD_TWID: after stage 0 the tile's coefficient 0 (register 0
+				 * of group-thread 0) is the one value no difference has scaled;
+				 * the caller multiplies it by n^-1 when it stores (a branch
+				 * here would make ptxas shuffle the whole register file to
+				 * merge the two paths: 34 moves per thread) */
 			}
 		}
 	}
