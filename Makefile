@@ -44,7 +44,7 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 
 .PHONY: all libs oracle refbins examples tools clean check check-host
 all: libs oracle refbins examples
-examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop $(BIN_DIR)/api_product
+examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop $(BIN_DIR)/api_product $(BIN_DIR)/api_e2e
 libs: $(SHARED) $(STATIC)
 refbins: $(REF_BINS)
 
@@ -88,6 +88,12 @@ $(BIN_DIR)/api_loop: examples/api_loop.c $(STATIC)
 
 # the reference's polynomial product sequence (recorded transforms + fused product)
 $(BIN_DIR)/api_product: examples/api_product.c $(STATIC)
+	@mkdir -p $(BIN_DIR)
+	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# the reference's 18 calls end to end from pageable host memory (bench.py's
+# e2e_reference_api)
+$(BIN_DIR)/api_e2e: examples/api_e2e.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
 

@@ -334,7 +334,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def bind_near_gpu(device):
@@ -615,7 +615,7 @@ def run_native_arm(args):
     # the same trip through the reference's 18 calls only (one vector per
     # polynomial, pageable host memory): copy_from_host, forward_transform,
     # inverse_transform, map (read the result), unmap.  A bounded sample:
-    # LEGACY_POLYS polynomials over this rank's limbs.
+    # LEGACY_POLYS polynomials over this rank's limbs, driven from Python ...
     legacy_polys = 64
     legacy_vecs = [ctx.vector(N, zero=False) for _ in range(legacy_polys)]
     legacy_in = np.array(host_in.array[:legacy_polys * N])   # pageable copy
@@ -629,19 +629,34 @@ def run_native_arm(args):
         for p, v in enumerate(legacy_vecs):
             ctx.inverse_transform(v, v, tables[p % own])
         for p, v in enumerate(legacy_vecs):
-            legacy_out[p * N:(p + 1) * N] = v.to_host()
+            v.read_into(legacy_out[p * N:(p + 1) * N])   # map, copy, unmap
 
     step_legacy()
     ctx.sync()
     barrier()
     t_legacy = time.perf_counter()
-    legacy_steps = 3
+    legacy_steps = 5
     for _ in range(legacy_steps):
         step_legacy()
     ctx.sync()
     t_legacy = max_over_ranks((time.perf_counter() - t_legacy) / legacy_steps)
     ok = ok and bool(np.array_equal(legacy_out, legacy_in))
     legacy_value = world * 2 * legacy_polys / t_legacy
+    # ... and from C, as the reference's own callers are (examples/api_e2e.c:
+    # the same five calls per vector, no interpreter between them)
+    legacy_c = None
+    api_e2e = os.path.join(ROOT, "build", "bin", "api_e2e")
+    if rank == 0 and os.path.exists(api_e2e):
+        try:
+            res = subprocess.run(
+                [api_e2e, str(LOG2N), str(legacy_polys), "8"],
+                env=dict(os.environ, VKHEL_DEVICE=str(local_rank)),
+                capture_output=True, text=True, timeout=120)
+            for text in res.stdout.splitlines():
+                if text.startswith("{"):
+                    legacy_c = json.loads(text)
+        except (OSError, ValueError, subprocess.SubprocessError):
+            legacy_c = None
 
     peaks = ctx.probe_int_peaks() if rank == 0 else None
     all_ok = max_over_ranks(0.0 if ok else 1.0) == 0.0
@@ -692,16 +707,21 @@ def run_native_arm(args):
                             "overlap with each other and with compute"},
             "e2e_ceiling": ceiling,
             "e2e_reference_api": {
-                "value": legacy_value, "unit": "NTT/s",
+                "value": (legacy_c["ntt_per_s"]
+                          if legacy_c and legacy_c.get("round_trip_exact")
+                          and world == 1 else legacy_value),
+                "unit": "NTT/s",
                 "sample": "%d polynomials per rank, one vkhel_vector each"
                           % legacy_polys,
+                "from_c": legacy_c, "from_python": legacy_value,
                 "path": "the reference's 18 entry points only, pageable host "
                         "memory: vkhel_vector_copy_from_host -> "
                         "vkhel_vector_forward_transform -> "
                         "vkhel_vector_inverse_transform -> vkhel_vector_map "
                         "+ copy out + vkhel_vector_unmap (which writes the "
                         "vector back, as the reference does); host wall "
-                        "clock"},
+                        "clock; value = the C caller (examples/api_e2e.c) at "
+                        "N = 1, the Python loop over all ranks otherwise"},
             # whole job: every rank launches the same kernels on its shard
             "gpu_launches": launches * world,
             "clocks": clocks,
@@ -732,7 +752,7 @@ def run_native_arm(args):
         line["issue_roofline"]["per"] = "GPU"
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(12.0)
-        print(json.dumps(line))
+        emit_line(line)
 
     timer.destroy()
     for v in [data, work] + slices[0] + slices[1] + legacy_vecs:
@@ -748,7 +768,23 @@ def run_native_arm(args):
         raise SystemExit("bench.py: parity / round trip mismatch -- result invalid")
 
 
+def emit_line(line):
+    """the one JSON line, on the process's real stdout"""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
+
+
 def main():
+    # Libraries print on stdout behind our back (the context's device banner,
+    # NCCL's version line at communicator creation, buffered until exit): keep
+    # the real stdout for the one JSON line and point fd 1 at stderr for
+    # everything else.
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

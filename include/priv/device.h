@@ -13,7 +13,7 @@
 extern "C" {
 #endif
 
-#define VKHEL_PINNED_SLOTS 8
+#define VKHEL_PINNED_SLOTS 16
 #define VKHEL_FORK_EVENTS 4
 
 struct pinned_slot {
@@ -25,6 +25,7 @@ struct pinned_slot {
 	 * waited for before the buffer is handed out again */
 	int busy;
 	void *event;
+	uint64_t released;  /* sequence number of the release (oldest is reused first) */
 };
 
 struct device_ctx {
@@ -61,6 +62,9 @@ struct device_ctx {
 	uint64_t deferred_transforms; /* transforms that went out in them */
 	uint64_t fused_products;      /* elemmul calls fused into the inverse that followed */
 	int stream_exposed;  /* vkhel_ctx_stream() handed the stream out: no more recording */
+	uint64_t pinned_seq; /* counter behind pinned_slot.released */
+	void *readahead;     /* results of the last recorded batch, for map() (opaque, C++) */
+	uint64_t readahead_hits;   /* maps served from a copy started before they were called */
 };
 
 void device_ctx_init(struct device_ctx *dev, int device);

@@ -40,6 +40,16 @@ struct vkhel_vector {
 	 * after everything on the compute stream) */
 	uint64_t last_op;
 	int exposed;
+	/* element range [map_offset, map_offset + host.bytes / 8) held by the
+	 * current map (vkhel_vector_map_range; the reference's map: everything) */
+	size_t map_offset;
+	/* read-ahead for map() (vector.cu): a device -> host copy of the whole
+	 * vector started before map() was called -- pinned buffer, the event
+	 * that ends the copy, and last_op at the time (any later operation on the
+	 * vector makes the copy stale) */
+	void *ra_ptr;
+	void *ra_event;     /* cudaEvent_t, created on first use */
+	uint64_t ra_op;
 };
 
 void vkhel_vector_dbgprint(const struct vkhel_vector *);

@@ -49,6 +49,17 @@ void *vkhel_host_alloc(size_t bytes);
 void vkhel_host_free(void *);
 uint64_t vkhel_vector_length(const struct vkhel_vector *);
 void *vkhel_vector_device_ptr(struct vkhel_vector *);
+/* vkhel_vector_map (reference src/vector.c:270-283) for the element range
+ * [offset, offset + count) only: stages and copies count*8 bytes instead of the
+ * whole vector; vkhel_vector_unmap writes that range back.  The reference's
+ * own map always moves the whole vector (its size argument is not usable, see
+ * vkhel.h). */
+void vkhel_vector_map_range(struct vkhel_vector *, void **mem,
+		uint64_t offset, uint64_t count);
+/* maps whose device -> host copy had been started before they were called: a
+ * map of a vector that a recorded batch of transforms produced also starts the
+ * copies of the next vectors of that batch (vector.cu, read-ahead) */
+uint64_t vkhel_ctx_readahead_hits(const struct vkhel_ctx *);
 /* enqueue copies of `count` elements starting at element `offset`; the host
  * buffer must stay valid until vkhel_ctx_sync / map / destroy */
 void vkhel_vector_upload(struct vkhel_vector *, const uint64_t *src,

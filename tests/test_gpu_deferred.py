@@ -377,3 +377,41 @@ def test_recorded_product_is_launched_when_anything_else_follows(ctx):
         v.destroy()
     t.destroy()
     t2.destroy()
+
+
+@pytest.mark.parametrize("log2n,mult", [(3, 1), (8, 1), (10, 5), (12, 1),
+                                        (14, 0), (16, 1), (16, 123456789)])
+def test_elemfma_followed_by_inverse_is_fused(ctx, log2n, mult):
+    """The point-wise ADD of the transform domain (reference
+    src/vector.c:298-340: elemfma, "modular add" when the multiplier is 1)
+    followed by the in-place inverse transform of its result: recorded like the
+    product and applied while the inverse transform loads, same result as the
+    separate launches.  Arbitrary 64-bit a, multipliers 0, 1, > 1 and >= q."""
+    n, q = 1 << log2n, params.P0
+    t = Tables(n, q)
+    rng = np.random.default_rng(100 + log2n + mult)
+    x = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    y = rand_mod(rng, n, q)
+    a, b, c = ctx.from_host(x), ctx.from_host(y), ctx.vector(n)
+    f0 = ctx.fused_products
+    for m in (mult, mult + q):                   # the multiplier is reduced mod q
+        ctx.elemfma(a, b, c, m % (1 << 64), q)
+        ctx.inverse_transform(c, c, t.lib)
+        want = oracle.inverse(oracle.elemfma(x, y, mult % q, q), t.ora)
+        assert np.array_equal(c.to_host(), want)
+    assert ctx.fused_products == f0 + 2
+    assert np.array_equal(a.to_host(), x) and np.array_equal(b.to_host(), y)
+    # accumulate in place, then transform: result aliases the addend
+    ctx.elemfma(a, b, b, 1, q)
+    ctx.inverse_transform(b, b, t.lib)
+    assert np.array_equal(
+        b.to_host(), oracle.inverse(oracle.elemfma(x, y, 1, q), t.ora))
+    assert ctx.fused_products == f0 + 3
+    # anything else in between: the sum is launched on its own
+    ctx.elemfma(a, b, c, 1, q)
+    got = c.to_host()
+    assert np.array_equal(got, oracle.elemfma(x, b.to_host(), 1, q))
+    assert ctx.fused_products == f0 + 3
+    for v in (a, b, c):
+        v.destroy()
+    t.destroy()

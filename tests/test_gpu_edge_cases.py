@@ -294,6 +294,70 @@ def test_ragged_rns_shapes(ctx, log2n, limbs, batch):
         t.destroy()
 
 
+def test_map_range_moves_only_its_range(ctx):
+    """vkhel_vector_map_range stages [offset, offset + count) and unmap
+    writes exactly that range back; the reference's map (the whole vector)
+    is the special case"""
+    data = np.arange(1000, dtype=np.uint64) * np.uint64(3)
+    v = ctx.from_host(data)
+    view = v.map_range(100, 50)
+    assert np.array_equal(view, data[100:150])
+    view[:] = np.arange(50, dtype=np.uint64) + np.uint64(7000)
+    v.unmap()
+    want = data.copy()
+    want[100:150] = np.arange(50, dtype=np.uint64) + np.uint64(7000)
+    assert np.array_equal(v.to_host(), want)
+    assert v.map_range(1000, 0).size == 0      # empty range at the end
+    v.unmap()
+    assert np.array_equal(v.map_range(0, 1000), want)
+    v.unmap()
+    v.destroy()
+
+
+def test_map_readahead_follows_a_recorded_batch():
+    """A loop of maps after a loop of (recorded) transforms: mapping one
+    result starts the device -> host copies of the next ones; every map still
+    returns the current contents -- a copy started before the vector was
+    modified again is not used."""
+    own = vk.Context(0)
+    n, q = 1 << 12, params.P0
+    tp = TablePair(n, q)
+    rng = np.random.default_rng(64)
+    xs = [rand_mod(rng, n, q) for _ in range(10)]
+    vs = [own.from_host(x) for x in xs]
+    for v in vs:
+        own.forward_transform(v, v, tp.lib)
+    want = [oracle.forward(x, tp.ora) for x in xs]
+    hits0 = own.readahead_hits
+    assert np.array_equal(vs[0].to_host(), want[0])     # starts copies of 1, 2, 3
+    # vector 2 changes after its copy was started: the copy is stale
+    own.elemmul(vs[2], vs[2], vs[2], q)
+    want[2] = oracle.elemmul(want[2], want[2], q)
+    # vector 3 is overwritten from the host through the async upload path
+    pinned = vk.host_alloc(n)
+    pinned.array[:] = xs[3]
+    vs[3].upload(pinned)
+    want[3] = xs[3]
+    for v, w in zip(vs[1:], want[1:]):
+        assert np.array_equal(v.to_host(), w)
+    assert own.readahead_hits - hits0 >= 5
+    # mapping again (nothing recorded since) and in reverse order still works
+    for v, w in zip(reversed(vs), reversed(want)):
+        assert np.array_equal(v.to_host(), w)
+    # a vector destroyed while its copy is in flight
+    for v in vs:
+        own.inverse_transform(v, v, tp.lib)
+    got = vs[0].to_host()
+    vs[1].destroy()
+    assert np.array_equal(vs[2].to_host(), oracle.inverse(want[2], tp.ora))
+    assert np.array_equal(got, xs[0])
+    for v in [vs[0]] + vs[2:]:
+        v.destroy()
+    pinned.free()
+    own.destroy()
+    tp.destroy()
+
+
 def test_map_sees_pending_upload_and_kernels(ctx):
     n = 4096
     tp = TablePair(n, params.P0)

@@ -534,3 +534,96 @@ def test_config5_sweep_roundtrip(ctx, log2n):
     tp = TablePair(n, params.P0)
     _roundtrip_and_linearity(ctx, [tp], n, batch, lambda p: params.P0)
     tp.destroy()
+
+
+# ---- BASELINE configs[3] and [4] at FULL size ------------------------------------------------------
+def _psi_powers(n, q, psi):
+    """psi^0 .. psi^(n-1) mod q"""
+    out = np.empty(n, np.uint64)
+    v = 1
+    for i in range(n):
+        out[i] = v
+        v = v * psi % q
+    return out
+
+
+def _evaluate_at_psi(polys, n, q, powers):
+    """a(psi) mod q for every polynomial of a [batch][n] array: the dot product
+    with the powers of psi (oracle mulmod, then an exact sum in two halves)"""
+    batch = polys.size // n
+    out = []
+    chunk = 64
+    for b0 in range(0, batch, chunk):
+        nb = min(chunk, batch - b0)
+        prod = oracle.elemmul(polys[b0 * n:(b0 + nb) * n], np.tile(powers, nb), q)
+        prod = prod.reshape(nb, n)
+        hi = (prod >> np.uint64(32)).sum(axis=1, dtype=np.uint64)
+        lo = (prod & np.uint64(0xffffffff)).sum(axis=1, dtype=np.uint64)
+        out += [((int(h) << 32) + int(l)) % q for h, l in zip(hi, lo)]
+    return out
+
+
+def test_config4_polymul_full_batch1024(ctx):
+    """BASELINE configs[3] at full size: n = 2^16, batch 1024, random a AND b
+    (512 MiB per operand).  Eight sampled products bit for bit against the
+    oracle's forward / elemmul / inverse, and EVERY product through a
+    size-independent identity: x^n + 1 vanishes at psi, so
+    c(psi) = a(psi) * b(psi) mod q."""
+    n, batch = 1 << 16, 1024
+    tp = TablePair(n, params.P0)
+    q = tp.q
+    rng = np.random.default_rng(1024)
+    a = rand_mod(rng, n * batch, q)
+    b = rand_mod(rng, n * batch, q)
+    va, vb, vc = ctx.from_host(a), ctx.from_host(b), ctx.vector(n * batch, zero=False)
+    ctx.polymul_rns(va, vb, vc, [tp.lib], batch)
+    got = vc.to_host()
+    assert np.array_equal(va.to_host(), a) and np.array_equal(vb.to_host(), b), \
+        "operands modified"
+    for v in (va, vb, vc):
+        v.destroy()
+    assert (got < np.uint64(q)).all(), "canonical output"
+    for p in (0, 1, 127, 128, 500, 777, 1022, 1023):
+        sl = slice(p * n, (p + 1) * n)
+        prod = oracle.elemmul(oracle.forward(a[sl], tp.ora),
+                              oracle.forward(b[sl], tp.ora), q)
+        assert np.array_equal(got[sl], oracle.inverse(prod, tp.ora)), p
+    powers = _psi_powers(n, q, tp.w)
+    ea = _evaluate_at_psi(a, n, q, powers)
+    eb = _evaluate_at_psi(b, n, q, powers)
+    ec = _evaluate_at_psi(got, n, q, powers)
+    bad = [p for p in range(batch) if ec[p] != ea[p] * eb[p] % q]
+    assert not bad, bad[:8]
+    tp.destroy()
+
+
+@pytest.mark.parametrize("log2n", [10, 17])
+def test_config5_sweep_full_size(ctx, log2n):
+    """BASELINE configs[4] at full size: 2^27 coefficients (1 GiB) at the two
+    ends of the sweep.  Every polynomial: canonical output, the evaluation
+    identity out[0] = a(psi) (output index 0 is the evaluation at psi^1,
+    SURVEY 8 a1) and the round trip; eight sampled polynomials bit for bit
+    against the oracle."""
+    n = 1 << log2n
+    batch = (1 << 27) >> log2n
+    tp = TablePair(n, params.P0)
+    q = tp.q
+    rng = np.random.default_rng(log2n)
+    x = rand_mod(rng, n * batch, q)
+    vx = ctx.from_host(x)
+    vf = ctx.vector(n * batch, zero=False)
+    ctx.forward_transform_batch(vx, vf, tp.lib, batch)
+    f = vf.to_host()
+    assert (f < np.uint64(q)).all(), "canonical output"
+    for p in sorted({0, 1, 2, batch // 3, batch // 2, batch - 3, batch - 2,
+                     batch - 1}):
+        sl = slice(p * n, (p + 1) * n)
+        assert np.array_equal(f[sl], oracle.forward(x[sl], tp.ora)), p
+    ex = _evaluate_at_psi(x, n, q, _psi_powers(n, q, tp.w))
+    first = f.reshape(batch, n)[:, 0]
+    bad = [p for p in range(batch) if int(first[p]) != ex[p]]
+    assert not bad, bad[:8]
+    del f
+    ctx.inverse_transform_batch(vf, vf, tp.lib, batch)
+    assert np.array_equal(vf.to_host(), x), "round trip"
+    vx.destroy(), vf.destroy(), tp.destroy()

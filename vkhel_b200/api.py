@@ -57,6 +57,8 @@ SIGNATURES = {
     "vkhel_host_free": (None, [_vp]),
     "vkhel_vector_length": (_u64, [_vp]),
     "vkhel_vector_device_ptr": (_vp, [_vp]),
+    "vkhel_vector_map_range": (None, [_vp, ctypes.POINTER(_vp), _u64, _u64]),
+    "vkhel_ctx_readahead_hits": (_u64, [_vp]),
     "vkhel_vector_upload": (None, [_vp, _vp, _u64, _u64]),
     "vkhel_vector_download": (None, [_vp, _vp, _u64, _u64]),
     "vkhel_vector_copy_peer": (None, [_vp, _u64, _vp, _u64, _u64]),
@@ -224,6 +226,26 @@ class Vector:
         lib().vkhel_vector_unmap(self.handle)
         return out
 
+    def map_range(self, offset, count):
+        """vkhel_vector_map_range: numpy view of the staged elements
+        [offset, offset + count); write to it, then unmap()"""
+        mem = _vp()
+        lib().vkhel_vector_map_range(self.handle, ctypes.byref(mem), offset,
+                                     count)
+        if not count:
+            return np.empty(0, np.uint64)
+        buf = (ctypes.c_uint64 * count).from_address(mem.value)
+        return np.frombuffer(buf, dtype=np.uint64)
+
+    def unmap(self):
+        lib().vkhel_vector_unmap(self.handle)
+
+    def read_into(self, out):
+        """map, copy the vector into `out` (a numpy array), unmap: the
+        reference's way to read a result, with one host copy"""
+        np.copyto(out, self.map_range(0, self.length))
+        self.unmap()
+
     def copy_peer(self, src, dst_offset=0, src_offset=0, count=None):
         """device -> device copy, possibly across GPUs (NVLink P2P)"""
         count = src.length - src_offset if count is None else count
@@ -301,6 +323,11 @@ class Context:
     def fused_products(self):
         """elemmul calls that were fused into the inverse transform after them"""
         return int(lib().vkhel_ctx_fused_products(self.handle))
+
+    @property
+    def readahead_hits(self):
+        """maps served from a device -> host copy started before the call"""
+        return int(lib().vkhel_ctx_readahead_hits(self.handle))
 
     @property
     def launch_count(self):

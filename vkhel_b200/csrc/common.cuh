@@ -111,11 +111,13 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 /* kernel launches of one transform launched by launch_ntt on the fast path */
 unsigned ntt_launches_per_transform(unsigned log2n);
 /* inverse transform of the point-wise product src * src2 (any 64-bit values,
- * reduced like the reference's elemmul); returns false when the fused kernel does not apply
- * and the caller has to multiply separately */
+ * reduced like the reference's elemmul) or, with fma_mult != 0 (already
+ * reduced mod q, q itself standing for 0; one modulus only), of
+ * src * fma_mult + src2 (elemfma); returns false when the fused kernel does not
+ * apply and the caller has to run the point-wise kernel separately */
 bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
-		uint64_t polys, unsigned log2n, uint64_t q_max);
+		uint64_t polys, unsigned log2n, uint64_t q_max, uint64_t fma_mult = 0);
 
 /* c = INTT(NTT(a) (*) NTT(b)) per polynomial with the row passes of the three
  * transforms and the product in one kernel; tmp holds polys << log2n words
@@ -143,5 +145,6 @@ void defer_flush(struct vkhel_ctx *ctx);
 void defer_flush_tables(struct vkhel_ctx *ctx,
 		const struct vkhel_ntt_tables *ntt);
 void defer_destroy(struct vkhel_ctx *ctx);
+void readahead_destroy(struct vkhel_ctx *ctx);
 
 #endif

@@ -145,6 +145,7 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	enter_device(dev->device);
 	/* struct vkhel_ctx is exactly its device_ctx (priv/vkhel.h) */
 	defer_destroy((struct vkhel_ctx *) dev);
+	readahead_destroy((struct vkhel_ctx *) dev);
 	registry_remove((struct vkhel_ctx *) dev);
 	cudaStream_t stream = (cudaStream_t) dev->stream;
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_h2d));
@@ -254,6 +255,10 @@ extern "C" uint64_t vkhel_ctx_fused_products(const struct vkhel_ctx *ctx) {
 	return ctx->dev.fused_products;
 }
 
+extern "C" uint64_t vkhel_ctx_readahead_hits(const struct vkhel_ctx *ctx) {
+	return ctx->dev.readahead_hits;
+}
+
 extern "C" void vkhel_ctx_flush(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
 	defer_flush(ctx);
@@ -317,8 +322,11 @@ static void pinned_slot_settle(struct pinned_slot *slot) {
 extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes) {
 	ctx_enter(ctx);
 	struct device_ctx *dev = &ctx->dev;
-	if (bytes == 0) {
-		bytes = 8;
+	/* small requests share one size class, so that the pieces of a staged
+	 * upload and the buffers of single-polynomial maps can use each other's
+	 * slots instead of replacing them */
+	if (bytes < ((size_t) 1 << 20)) {
+		bytes = (size_t) 1 << 20;
 	}
 	/* In order: a cached buffer that is large enough and idle; for small
 	 * requests a fresh buffer in an empty slot (so that consecutive staged
@@ -332,19 +340,27 @@ extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes) {
 		if (slot->in_use) {
 			continue;
 		}
+
 		if (!slot->ptr) {
 			empty = empty < 0 ? i : empty;
 		} else if (slot->bytes >= bytes) {
 			if (!slot->busy) {
 				fit = fit < 0 ? i : fit;
-			} else {
-				fit_busy = fit_busy < 0 ? i : fit_busy;
+			} else if (fit_busy < 0
+					|| slot->released < dev->pinned[fit_busy].released) {
+				/* the copy that was enqueued first ends first: waiting for
+				 * the most recent one would serialise staging and DMA */
+				fit_busy = i;
 			}
 		} else {
 			victim = victim < 0 ? i : victim;
 		}
 	}
-	if (fit < 0 && fit_busy >= 0 && (bytes > small || empty < 0)) {
+	if (fit < 0 && fit_busy >= 0 && (bytes > small || empty < 0
+				|| cudaEventQuery((cudaEvent_t) dev->pinned[fit_busy].event)
+					== cudaSuccess)) {
+		/* (the oldest busy buffer is often idle by now: one query instead of
+		 * a fresh allocation) */
 		fit = fit_busy;
 	}
 	if (fit >= 0) {
@@ -403,6 +419,7 @@ extern "C" void pinned_release_after(struct vkhel_ctx *ctx, void *ptr,
 						(cudaStream_t) stream));
 			slot->busy = 1;
 			slot->in_use = 0;
+			slot->released = ++dev->pinned_seq;
 			return;
 		}
 	}

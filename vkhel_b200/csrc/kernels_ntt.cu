@@ -334,7 +334,8 @@ static void run_generic(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 
 struct fast_pass {
 	const u64 *src;
-	const u64 *src2;      /* row pass, MUL: second factor of the point-wise product */
+	const u64 *src2;      /* row pass, MUL: second operand of the fused point-wise op */
+	u64 fma_mult;         /* MUL: 0 = product src*src2, else src*fma_mult + src2 */
 	u64 *dst;
 	const limb_desc *descs;
 	unsigned limbs;
@@ -409,6 +410,36 @@ __device__ __forceinline__ void static_for(F &&f) {
 		f(std::integral_constant<int, I>());
 		static_for<I + 1, N>(f);
 	}
+}
+
+/* The point-wise operation fused into the load of an inverse transform's first
+ * pass: the reference's elemmul (elemmul.comp:62-73) or elemfma (contract
+ * (a*mult + b) mod q) between the forward and the inverse
+ * transform (src/vector.c:298-340,388-427).  Exact for ANY 64-bit operands,
+ * like the stand-alone kernels (kernels_elem.cu): the result is the canonical
+ * residue those would have stored.  `fma_mult` = 0 selects the product,
+ * otherwise x*fma_mult + y with fma_mult already reduced mod q (a multiplier
+ * that is 0 mod q is passed as q: a*q + b = b mod q). */
+__device__ __forceinline__ u64 fused_pointwise(u64 x, u64 y, u64 fma_mult,
+		const modulus &m) {
+	if (fma_mult) {
+		/* the high word of x*mult is at most mult - 1 <= q - 1 and the carry
+		 * of the addition raises it to at most q: one conditional reduction */
+		const u64 lo = x * fma_mult;
+		const u64 sum = lo + y;
+		u64 hi = __umul64hi(x, fma_mult) + (sum < lo);
+		if (hi >= m.q) {
+			hi -= m.q;
+		}
+		return reduce128(hi, sum, m);
+	}
+	/* (x mod q)(y mod q) mod q: the high word is reduced first when it is not
+	 * already below q -- a branch canonical factors never take */
+	u64 hi = __umul64hi(x, y);
+	if (hi >= m.q) {
+		hi = reduce128(0, hi, m);
+	}
+	return reduce128(hi, x * y, m);
 }
 
 /* ---- programmatic dependent launch (PDL) ------------------------------------------
@@ -683,15 +714,7 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					const u64 y = active[pp] ? sp2[G::eoff(first, e)] : 0;
-					/* (x mod q)(y mod q) mod q for ANY 64-bit factors, like
-					 * the reference's elemmul (elemmul.comp:62-73): the high
-					 * word is reduced first when it is not already below q --
-					 * a branch canonical factors never take */
-					u64 hi = __umul64hi(x[pp][e], y);
-					if (hi >= q) {
-						hi = reduce128(0, hi, m);
-					}
-					x[pp][e] = reduce128(hi, x[pp][e] * y, m);
+					x[pp][e] = fused_pointwise(x[pp][e], y, p.fma_mult, m);
 				}
 			}
 		}
@@ -1067,11 +1090,7 @@ ntt_single_kernel(const __grid_constant__ fast_pass p) {
 #pragma unroll
 			for (int e = 0; e < 8; e++) {
 				const u64 y = sp2[G::eoff(first, e)];
-				u64 hi = __umul64hi(x[0][e], y);
-				if (hi >= q) {
-					hi = reduce128(0, hi, m);
-				}
-				x[0][e] = reduce128(hi, x[0][e] * y, m);
+				x[0][e] = fused_pointwise(x[0][e], y, p.fma_mult, m);
 			}
 		}
 		if (!tw_ready) {
@@ -1681,10 +1700,11 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL,
 		unsigned limbs_total = 0, unsigned limb0 = 0,
-		const ntt_ptrs *inline_tab = NULL) {
+		const ntt_ptrs *inline_tab = NULL, u64 fma_mult = 0) {
 	const fast_plan pl = plan_fast(log2n, !INV);
 	fast_pass p;
 	p.zero = 0;
+	p.fma_mult = fma_mult;
 	p.tab = tab;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -1828,6 +1848,7 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	const fast_plan pl = plan_fast(log2n);
 	fast_pass p;
 	p.zero = 0;
+	p.fma_mult = 0;
 	p.tab = NULL;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -2030,15 +2051,18 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 
 bool launch_ntt_inverse_of_product(struct vkhel_ctx *ctx, const u64 *src,
 		const u64 *src2, u64 *dst, const limb_desc *descs, uint64_t limbs,
-		uint64_t polys, unsigned log2n, uint64_t q_max) {
+		uint64_t polys, unsigned log2n, uint64_t q_max, uint64_t fma_mult) {
 	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
 	if (q_max >= (1ull << 62) || log2n < 3 || force_generic) {
 		return false;   /* generic path: no fused product */
 	}
+	VK_REQUIRE(!fma_mult || limbs == 1, "internal: fused fma is single-modulus");
 	if (use_approx(q_max, log2n)) {
-		run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+		run_fast<true, true>(ctx, src, dst, descs, limbs, polys, log2n, src2,
+				NULL, 0, 0, NULL, fma_mult);
 	} else {
-		run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n, src2);
+		run_fast<true, false>(ctx, src, dst, descs, limbs, polys, log2n, src2,
+				NULL, 0, 0, NULL, fma_mult);
 	}
 	return true;
 }

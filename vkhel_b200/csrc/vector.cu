@@ -55,14 +55,17 @@ static inline u64 *dev_u64_nodefer(const struct vkhel_vector *v) {
 struct defer_item {
 	ntt_ptrs ptrs;
 	unsigned table;     /* index into defer_queue::tables */
+	struct vkhel_vector *result;   /* for map()'s read-ahead */
 };
 
-/* A recorded vkhel_vector_elemmul, see "recorded product" below */
+/* A recorded vkhel_vector_elemmul or vkhel_vector_elemfma, see "recorded
+ * product" below */
 struct pending_product {
 	bool active;
+	bool fma;             /* a*multiplier + b instead of a*b */
 	const struct vkhel_vector *a, *b;
 	struct vkhel_vector *result;
-	uint64_t mod;
+	uint64_t mod, multiplier;
 };
 
 struct defer_queue {
@@ -141,6 +144,107 @@ static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 
 static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq);
 
+/* ---- read-ahead for map() ------------------------------------------------------------
+ * The reference reads results by mapping one vector after the other
+ * (src/vector.c:270-283: a device -> host copy and a fence wait per map).  A
+ * loop of transforms over separate vectors is recorded and launched as one
+ * batch (above); the loop of maps that follows would still pay one copy + one
+ * wait each, back to back with the caller's own read of the data.  So the
+ * context remembers the result vectors of the batch it launched last, and a
+ * map() of one of them also starts the device -> host copies of the next
+ * READAHEAD_WINDOW ones on the D2H stream; their maps then find the data on
+ * its way (or there) instead of starting from nothing.  A copy is used only if
+ * no operation has touched its vector since it was started (ra_op), and costs
+ * at most READAHEAD_WINDOW vector copies when the caller stops mapping. */
+#define READAHEAD_WINDOW 3
+
+struct readahead_list {
+	std::vector<struct vkhel_vector *> results;
+};
+
+static readahead_list *readahead_get(struct vkhel_ctx *ctx) {
+	if (!ctx->dev.readahead) {
+		ctx->dev.readahead = new readahead_list();
+	}
+	return (readahead_list *) ctx->dev.readahead;
+}
+
+/* give up a speculative copy (stale, or the vector goes away) */
+static void readahead_drop(struct vkhel_vector *vec) {
+	if (vec->ra_ptr) {
+		/* the copy may still be writing the buffer */
+		pinned_release_after(vec->ctx, vec->ra_ptr, vec->ctx->dev.stream_d2h);
+		vec->ra_ptr = NULL;
+	}
+}
+
+static void readahead_forget(struct vkhel_vector *vec) {
+	readahead_drop(vec);
+	readahead_list *ra = (readahead_list *) vec->ctx->dev.readahead;
+	if (ra) {
+		for (struct vkhel_vector *&v : ra->results) {
+			if (v == vec) {
+				v = NULL;
+			}
+		}
+	}
+}
+
+void readahead_destroy(struct vkhel_ctx *ctx) {
+	delete (readahead_list *) ctx->dev.readahead;
+	ctx->dev.readahead = NULL;
+}
+
+static void xfer_begin(struct vkhel_vector *vec, cudaStream_t copy);
+static void xfer_end(struct vkhel_vector *vec, cudaStream_t copy);
+
+/* start the device -> host copy of the whole vector into a fresh staging
+ * buffer; the event in ra_event marks its end */
+static void readahead_start(struct vkhel_vector *vec) {
+	struct vkhel_ctx *ctx = vec->ctx;
+	cudaStream_t copy = (cudaStream_t) ctx->dev.stream_d2h;
+	vec->ra_ptr = pinned_acquire(ctx, vec->device.bytes);
+	vec->ra_op = vec->last_op;
+	if (!vec->ra_event) {
+		cudaEvent_t ev;
+		CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		vec->ra_event = ev;
+	}
+	xfer_begin(vec, copy);
+	CUDA_CHECK(cudaMemcpyAsync(vec->ra_ptr, vec->device.ptr, vec->device.bytes,
+				cudaMemcpyDeviceToHost, copy));
+	xfer_end(vec, copy);
+	CUDA_CHECK(cudaEventRecord((cudaEvent_t) vec->ra_event, copy));
+}
+
+/* map() of `vec` has just been served: start the copies of the vectors that
+ * were recorded after it */
+static void readahead_advance(struct vkhel_vector *vec) {
+	static const bool off = getenv("VKHEL_NO_READAHEAD") != NULL;
+	readahead_list *ra = (readahead_list *) vec->ctx->dev.readahead;
+	if (off || !ra) {
+		return;
+	}
+	size_t at = 0;
+	while (at < ra->results.size() && ra->results[at] != vec) {
+		at++;
+	}
+	struct vkhel_vector *todo[READAHEAD_WINDOW];
+	int count = 0;
+	for (size_t i = at + 1; i < ra->results.size()
+			&& i <= at + READAHEAD_WINDOW; i++) {
+		struct vkhel_vector *next = ra->results[i];
+		if (next && !next->host.ptr && next->length
+				&& !(next->ra_ptr && next->ra_op == next->last_op)) {
+			todo[count++] = next;
+		}
+	}
+	for (int i = 0; i < count; i++) {
+		readahead_drop(todo[i]);
+		readahead_start(todo[i]);
+	}
+}
+
 void defer_flush(struct vkhel_ctx *ctx) {
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
 	if (!dq) {
@@ -155,6 +259,14 @@ void defer_flush(struct vkhel_ctx *ctx) {
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
 	const size_t count = dq->items.size();
 	const size_t ntab = dq->tables.size();
+	/* the vectors a loop of maps is likely to ask for next (read-ahead) */
+	readahead_list *ra = readahead_get(ctx);
+	ra->results.clear();
+	if (count > 1) {
+		for (const defer_item &it : dq->items) {
+			ra->results.push_back(it.result);
+		}
+	}
 	/* An indirect batch costs a pointer-table copy on top of its launches;
 	 * a record that short is cheaper launched transform by transform:
 	 * always a single one, and two where a transform is one launch (the
@@ -290,6 +402,7 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 	item.ptrs.src = dev_u64_nodefer(operand);
 	item.ptrs.dst = dev_u64_nodefer(result);
 	item.table = table;
+	item.result = result;
 	dq->inverse = inverse;
 	dq->log2n = ntt->log2n;
 	dq->items.push_back(item);
@@ -327,8 +440,14 @@ static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq) {
 	dq->mul.active = false;
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
 	const pending_product &m = dq->mul;
-	launch_elemmul(ctx, dev_u64_nodefer(m.a), dev_u64_nodefer(m.b),
-			dev_u64_nodefer(m.result), m.result->length, m.mod);
+	if (m.fma) {
+		launch_elemfma(ctx, dev_u64_nodefer(m.a), dev_u64_nodefer(m.b),
+				dev_u64_nodefer(m.result), m.result->length, m.multiplier,
+				m.mod);
+	} else {
+		launch_elemmul(ctx, dev_u64_nodefer(m.a), dev_u64_nodefer(m.b),
+				dev_u64_nodefer(m.result), m.result->length, m.mod);
+	}
 }
 
 /* the inverse transform that follows a recorded product: true when the fused
@@ -346,10 +465,17 @@ static bool fuse_product_into_inverse(const struct vkhel_vector *operand,
 		return false;   /* the caller's path launches the product first */
 	}
 	dq->mul.active = false;
+	/* elemfma: the multiplier reduced mod q, with q standing for 0 (the
+	 * kernel reads 0 as "product") */
+	uint64_t fma_mult = 0;
+	if (m.fma) {
+		fma_mult = m.multiplier % m.mod;
+		fma_mult = fma_mult ? fma_mult : m.mod;
+	}
 	if (launch_ntt_inverse_of_product(ctx, dev_u64_nodefer(m.a),
 				dev_u64_nodefer(m.b), dev_u64_nodefer(result),
 				ntt_tables_device_desc(ctx, ntt), 1, 1, (unsigned) ntt->log2n,
-				ntt->q)) {
+				ntt->q, fma_mult)) {
 		ctx->dev.fused_products++;
 		return true;
 	}
@@ -437,10 +563,15 @@ extern "C" void vkhel_vector_destroy(struct vkhel_vector *vec) {
 		return;
 	}
 	struct vkhel_ctx *ctx = vec->ctx;
+	enter(ctx);
 	if (vec->host.ptr) {
 		/* destroyed while mapped: drop the staging buffer, nothing is
 		 * written back */
 		pinned_release(ctx, vec->host.ptr);
+	}
+	readahead_forget(vec);
+	if (vec->ra_event) {
+		CUDA_CHECK(cudaEventDestroy((cudaEvent_t) vec->ra_event));
 	}
 	/* stream-ordered free: work already enqueued on the stream (and any
 	 * transfer still in flight) completes before the block is reused */
@@ -464,15 +595,20 @@ extern "C" struct vkhel_vector *vkhel_vector_dup(struct vkhel_vector *src) {
 	return dup;
 }
 
-/* chunk of the staged host -> device copies below */
-#define STAGE_CHUNK_BYTES ((size_t) 8 << 20)
+/* piece of the staged host -> device copies below.  Measured from C on the
+ * B200 box (examples/api_e2e.c, 64 polynomials of 512 KiB per step): every
+ * piece costs about 10 us of calls (copy, event, slot search) next to 27 us of
+ * memcpy per 512 KiB, and in a loop over vectors the DMA of one vector overlaps
+ * the memcpy of the next whatever the piece size -- so one piece per
+ * polynomial of n = 2^16, several for anything larger. */
+#define STAGE_CHUNK_BYTES ((size_t) 512 << 10)
 
 extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 		const uint64_t *elements) {
 	/* The reference maps (a device->host copy it does not need), memcpys and
 	 * unmaps (vector.c:262-268).  Here: one host->device copy.  The source
 	 * may be pageable and may be reused by the caller as soon as this
-	 * returns, so it is copied into pinned staging buffers (chunks of 8 MiB
+	 * returns, so it is copied into pinned staging buffers (pieces of 512 KiB
 	 * from the context's cache, each released when its transfer has ended)
 	 * and the transfers are left in flight: the call neither waits for them
 	 * nor for the kernels enqueued before it. */
@@ -497,32 +633,61 @@ extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 	}
 }
 
+extern "C" void vkhel_vector_map_range(struct vkhel_vector *vec, void **mem,
+		uint64_t offset, uint64_t count) {
+	VK_REQUIRE(!vec->host.ptr, "vector is already mapped");
+	VK_REQUIRE(offset + count <= vec->length && offset + count >= offset,
+			"map_range out of range");
+	struct vkhel_ctx *ctx = vec->ctx;
+	enter(ctx);
+	defer_flush(ctx);
+	const bool whole = offset == 0 && count == vec->length;
+	vec->map_offset = offset;
+	vec->host.bytes = count * sizeof(uint64_t);
+	if (whole && vec->ra_ptr && vec->ra_op == vec->last_op) {
+		/* a read-ahead copy of exactly this state of the vector */
+		CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) vec->ra_event));
+		vec->host.ptr = vec->ra_ptr;
+		vec->ra_ptr = NULL;
+		ctx->dev.readahead_hits++;
+	} else {
+		readahead_drop(vec);
+		vec->host.ptr = pinned_acquire(ctx, vec->host.bytes);
+		if (count) {
+			/* on the D2H stream, behind the last operation that touched this
+			 * vector: only that is waited for, not whatever else the compute
+			 * stream holds */
+			cudaStream_t copy = (cudaStream_t) ctx->dev.stream_d2h;
+			xfer_begin(vec, copy);
+			CUDA_CHECK(cudaMemcpyAsync(vec->host.ptr,
+						(u64 *) vec->device.ptr + offset, vec->host.bytes,
+						cudaMemcpyDeviceToHost, copy));
+			xfer_end(vec, copy);
+			CUDA_CHECK(cudaStreamSynchronize(copy));
+		}
+	}
+	if (whole) {
+		readahead_advance(vec);
+	}
+	*mem = vec->host.ptr;
+}
+
 extern "C" void vkhel_vector_map(struct vkhel_vector *vec, void **mem,
 		size_t size) {
 	/* `size` is in bytes in the reference's tests and in elements in its
 	 * example; staging the whole vector serves both. */
 	(void) size;
-	VK_REQUIRE(!vec->host.ptr, "vector is already mapped");
-	enter(vec->ctx);
-	vec->host.bytes = vec->device.bytes;
-	vec->host.ptr = pinned_acquire(vec->ctx, vec->host.bytes);
-	if (vec->length) {
-		CUDA_CHECK(cudaMemcpyAsync(vec->host.ptr, dev_u64(vec),
-					vec->device.bytes, cudaMemcpyDeviceToHost,
-					ctx_stream(vec->ctx)));
-	}
-	/* everything enqueued before the map is now visible to the host */
-	CUDA_CHECK(cudaStreamSynchronize(ctx_stream(vec->ctx)));
-	*mem = vec->host.ptr;
+	vkhel_vector_map_range(vec, mem, 0, vec->length);
 }
 
 extern "C" void vkhel_vector_unmap(struct vkhel_vector *vec) {
 	VK_REQUIRE(vec->host.ptr, "vector is not mapped");
 	enter(vec->ctx);
-	/* the whole vector is written back (reference vector.c:291) */
-	if (vec->length) {
-		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec), vec->host.ptr,
-					vec->device.bytes, cudaMemcpyHostToDevice,
+	/* what was mapped is written back (reference vector.c:291: the whole
+	 * vector; a sub-range map writes back its range) */
+	if (vec->host.bytes) {
+		CUDA_CHECK(cudaMemcpyAsync(dev_u64(vec) + vec->map_offset, vec->host.ptr,
+					vec->host.bytes, cudaMemcpyHostToDevice,
 					ctx_stream(vec->ctx)));
 	}
 	/* the staging buffer goes back to the cache and is handed out again only
@@ -530,6 +695,7 @@ extern "C" void vkhel_vector_unmap(struct vkhel_vector *vec) {
 	pinned_release_after(vec->ctx, vec->host.ptr, ctx_stream(vec->ctx));
 	vec->host.ptr = NULL;
 	vec->host.bytes = 0;
+	vec->map_offset = 0;
 }
 
 extern "C" void vkhel_vector_dbgprint(const struct vkhel_vector *vec) {
@@ -566,6 +732,7 @@ extern "C" void vkhel_vector_upload(struct vkhel_vector *vec,
 	enter(vec->ctx);
 	if (count) {
 		cudaStream_t copy = (cudaStream_t) vec->ctx->dev.stream_h2d;
+		readahead_drop(vec);   /* the vector changes: a copy taken earlier is stale */
 		xfer_begin(vec, copy);
 		CUDA_CHECK(cudaMemcpyAsync((u64 *) vec->device.ptr + offset, src,
 					count * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
@@ -644,6 +811,34 @@ extern "C" void vkhel_vector_copy_peer(struct vkhel_vector *dst,
 /* ---- element-wise entry points ------------------------------------------------
  * As in the reference every op runs over result->length elements and operand
  * lengths are not checked (src/kernels/elemmul.c:164,173-174). */
+/* Record a point-wise product or fma as the candidate for the fused
+ * inverse-of-product (see "recorded product" above): true when it is held
+ * back, false when the caller has to launch it. */
+static bool record_pointwise(bool fma, const struct vkhel_vector *a,
+		const struct vkhel_vector *b, struct vkhel_vector *result,
+		uint64_t multiplier, uint64_t mod) {
+	static const bool off = getenv("VKHEL_NO_DEFER") != NULL
+		|| getenv("VKHEL_NO_FUSED_PRODUCT") != NULL;
+	/* candidates: a power-of-two length the fast transform path covers */
+	const uint64_t len = result->length;
+	const bool exposed = result->ctx->dev.stream_exposed || a->exposed
+		|| b->exposed || result->exposed;   /* see defer_transform */
+	if (off || exposed || len < 8 || (len & (len - 1)) != 0
+			|| mod >= (1ull << 62)) {
+		return false;
+	}
+	defer_flush(result->ctx);   /* what was recorded so far goes first */
+	defer_queue *dq = defer_get(result->ctx);
+	dq->mul.active = true;
+	dq->mul.fma = fma;
+	dq->mul.a = a;
+	dq->mul.b = b;
+	dq->mul.result = result;
+	dq->mul.mod = mod;
+	dq->mul.multiplier = multiplier;
+	return true;
+}
+
 extern "C" void vkhel_vector_elemfma(
 		const struct vkhel_vector *a, const struct vkhel_vector *b,
 		struct vkhel_vector *result, uint64_t multiplier, uint64_t mod) {
@@ -655,6 +850,13 @@ extern "C" void vkhel_vector_elemfma(
 			multiplier, mod);
 	DBG_VEC("a", a);
 	DBG_VEC("b", b);
+	/* "modular add" (multiplier 1) or a scaled accumulation in the transform
+	 * domain, followed by the in-place inverse transform: recorded like the
+	 * product and folded into that transform's first load */
+	if (record_pointwise(true, a, b, result, multiplier, mod)) {
+		DBG_VEC("result", result);
+		return;
+	}
 	launch_elemfma(result->ctx, dev_u64(a), dev_u64(b), dev_u64(result),
 			result->length, multiplier, mod);
 	DBG_VEC("result", result);
@@ -670,22 +872,7 @@ extern "C" void vkhel_vector_elemmul(
 	DBG("elemmul mod: %" PRIu64 "\n", mod);
 	DBG_VEC("a", a);
 	DBG_VEC("b", b);
-	static const bool off = getenv("VKHEL_NO_DEFER") != NULL
-		|| getenv("VKHEL_NO_FUSED_PRODUCT") != NULL;
-	/* candidates for the fused inverse-of-product: a power-of-two length the
-	 * fast transform path covers */
-	const uint64_t len = result->length;
-	const bool exposed = result->ctx->dev.stream_exposed || a->exposed
-		|| b->exposed || result->exposed;   /* see defer_transform */
-	if (!off && !exposed && len >= 8 && (len & (len - 1)) == 0
-			&& mod < (1ull << 62)) {
-		defer_flush(result->ctx);   /* what was recorded so far goes first */
-		defer_queue *dq = defer_get(result->ctx);
-		dq->mul.active = true;
-		dq->mul.a = a;
-		dq->mul.b = b;
-		dq->mul.result = result;
-		dq->mul.mod = mod;
+	if (record_pointwise(false, a, b, result, 0, mod)) {
 		DBG_VEC("result", result);
 		return;
 	}
