@@ -6,7 +6,11 @@ The environment switches $VKHEL_EXACT_QUOTIENT and $VKHEL_FORCE_GENERIC force
 the slower families for every modulus, $VKHEL_POLYMUL_UNFUSED the polynomial
 product as separate transforms, $VKHEL_NO_DEFER immediate launches of the
 single-vector transforms, $VKHEL_SINGLE_MAX_LOG2N the sizes that take the
-single-pass kernel (8 = none, 12 = one more than the default) and
+single-pass kernel (8 = none, 12 and 13 = beyond the default),
+$VKHEL_CLUSTER=1 sends 2^14 <= n <= 2^16 through the thread-block-cluster
+kernel (kernels_ntt_cluster.cu; more shapes in tests/test_gpu_cluster.py),
+$VKHEL_COLS_TMA=1 loads the forward column tiles of n = 2^16 by TMA tensor map
+(kernels_ntt_tma.cu) and
 $VKHEL_SLICE_MIB=0.0625 cuts every two-pass batch above 192 KiB into slices on two
 streams; they are read once per process, so the parity tests are re-run in
 child processes."""
@@ -30,6 +34,9 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
                                     "VKHEL_NO_DEFER",
                                     "VKHEL_SINGLE_MAX_LOG2N=8",
                                     "VKHEL_SINGLE_MAX_LOG2N=12",
+                                    "VKHEL_SINGLE_MAX_LOG2N=13",
+                                    "VKHEL_CLUSTER=1",
+                                    "VKHEL_COLS_TMA=1",
                                     "VKHEL_SLICE_MIB=0.0625"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)

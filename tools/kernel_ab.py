@@ -18,7 +18,7 @@ sys.path.insert(0, %r)
 import numpy as np
 import vkhel_b200 as vk
 from vkhel_b200 import params
-N, LIMBS, BATCH = 1 << 16, 32, 16
+N, LIMBS, BATCH = 1 << 16, int(os.environ.get("AB_LIMBS", "32")), 16
 primes = params.ntt_primes(LIMBS)
 ctx = vk.Context(0)
 tabs = [vk.NttTables(N, q, params.find_psi(N, q), ctx=ctx) for q in primes]

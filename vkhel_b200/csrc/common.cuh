@@ -139,6 +139,21 @@ void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
 		uint64_t polys, unsigned log2n, uint64_t q_max,
 		const ntt_ptrs *host_tab = NULL);
 
+/* kernels_ntt_cluster.cu: single-pass transform of 2^14 <= n <= 2^16 on a
+ * thread-block cluster (polynomial distributed over the CTAs' shared memory);
+ * same arguments as the fast path of launch_ntt */
+bool ntt_cluster_enabled(unsigned log2n);
+void launch_ntt_cluster(struct vkhel_ctx *ctx, bool inverse, bool apx,
+		const u64 *src, u64 *dst, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, unsigned limbs_total, unsigned limb0);
+
+/* kernels_ntt_tma.cu: the forward column pass of n = 2^16 with its tile loaded
+ * by one TMA tensor-map copy instead of per-thread loads (opt-in variant) */
+bool ntt_cols_tma_enabled(unsigned log2n, unsigned kcol, unsigned s0);
+void launch_ntt_cols_tma(struct vkhel_ctx *ctx, bool apx, const u64 *src,
+		u64 *dst, const limb_desc *descs, uint64_t limbs, uint64_t polys,
+		unsigned limbs_total, unsigned limb0);
+
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */
 void defer_flush(struct vkhel_ctx *ctx);
