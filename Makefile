@@ -45,7 +45,8 @@ REF_BINS := $(if $(wildcard $(REF)/test/vector.c), \
 
 .PHONY: all libs oracle refbins examples tools clean check check-host
 all: libs oracle refbins examples
-examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop $(BIN_DIR)/api_product $(BIN_DIR)/api_e2e
+examples: $(BIN_DIR)/multi_gpu $(BIN_DIR)/api_loop $(BIN_DIR)/api_product $(BIN_DIR)/api_e2e \
+          $(BIN_DIR)/vulkan_dump
 libs: $(SHARED) $(STATIC)
 refbins: $(REF_BINS)
 
@@ -97,6 +98,12 @@ $(BIN_DIR)/api_product: examples/api_product.c $(STATIC)
 $(BIN_DIR)/api_e2e: examples/api_e2e.c $(STATIC)
 	@mkdir -p $(BIN_DIR)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ $(STATIC) $(CUDA_LIBS)
+
+# the dump program of tools/vulkan_parity.sh, here against THIS library (the
+# same program linked against the meson-built reference shows the shaders)
+$(BIN_DIR)/vulkan_dump: tools/vulkan_dump.c $(SHARED)
+	@mkdir -p $(BIN_DIR)
+	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ -L$(LIB_DIR) -lvkhel -Wl,-rpath,'$$ORIGIN/../../$(LIB_DIR)'
 
 # micro-benchmarks behind the roofline denominators (profiles/*bench*.txt)
 tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench $(BIN_DIR)/exchange_bench

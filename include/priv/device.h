@@ -40,6 +40,18 @@ struct device_ctx {
 	void *stream_aux;    /* second compute stream for sliced transforms */
 	void *ev_aux;        /* fork/join event of the sliced transforms */
 	void *launch_stream; /* non-NULL while kernels go to stream_aux */
+	/* Lazy join of a sliced transform (kernels_ntt.cu, run_fast_sliced): the
+	 * odd slices of the last sliced transform are still un-joined on
+	 * stream_aux.  The next sliced transform onto the same vector with the
+	 * same partition continues slice by slice on the same two streams; anything
+	 * else joins first (defer_flush).  split_hold: set by the batched transform
+	 * entry points while they fetch their pointers, so that this one flush does
+	 * not join. */
+	int split_active, split_hold, split_by_limb;
+	const void *split_dst;
+	size_t split_bytes;
+	uint64_t split_per, split_units;
+	unsigned split_log2n;
 	/* Every use of a vector on the compute stream takes the next serial
 	 * number; fork_ev[i] was recorded on the compute stream when the serial
 	 * stood at fork_serial[i], so it covers every use up to that number.  A

@@ -415,3 +415,75 @@ def test_dbgprint_symbols(ctx, capfd):
     assert "1, 2, 3" in out
     assert "ntt_tables: (n=4 q=113 w=18)" in out and "1, 98, 18, 69" in out
     v.destroy(), t.destroy()
+
+
+def test_sliced_transforms_chain_without_joins_and_join_when_needed(ctx):
+    """An RNS batch of at least 8 MiB is transformed as limb slices on two
+    streams, and the join of the two streams is left to whoever needs the
+    context next (lazy join, kernels_ntt.cu): a chain of transforms over the
+    same vector continues slice by slice, everything else -- another operation
+    on the vector, a transfer, a recorded single-vector transform, another
+    partition, another destination -- has to see all slices finished."""
+    n, limbs, batch = 1 << 14, 4, 16                       # 8 MiB
+    primes = params.ntt_primes(limbs)
+    tps = [TablePair(n, q) for q in primes]
+    libs, oras = [t.lib for t in tps], [t.ora for t in tps]
+    rng = np.random.default_rng(88)
+    x = np.concatenate([rand_mod(rng, n, primes[p % limbs])
+                        for p in range(limbs * batch)])
+    fx = oracle.forward_batch(x, oras, threads=8)
+    data, work = ctx.from_host(x), ctx.vector(x.size, zero=False)
+    # a chain: forward out of place, inverse / forward in place, several times
+    for _ in range(3):
+        ctx.forward_transform_rns(data, work, libs, batch)
+        ctx.inverse_transform_rns(work, work, libs, batch)
+    ctx.forward_transform_rns(work, work, libs, batch)
+    assert np.array_equal(work.to_host(), fx)              # map joins
+    # an element-wise operation right behind the slices
+    ctx.inverse_transform_rns(work, work, libs, batch)
+    ctx.elemgtadd(work, work, 0, 0)                        # identity, must join
+    assert np.array_equal(work.to_host(), x)
+    # another destination, then another partition of the same vector
+    other = ctx.vector(x.size, zero=False)
+    ctx.forward_transform_rns(work, work, libs, batch)
+    ctx.inverse_transform_rns(work, other, libs, batch)
+    assert np.array_equal(other.to_host(), x)
+    ctx.forward_transform_rns(data, work, libs, batch)
+    ctx.inverse_transform_rns(work, work, libs[:2] * 2, batch)   # not the tables it was made with
+    ctx.forward_transform_rns(work, work, libs[:2] * 2, batch)
+    assert np.array_equal(work.to_host(), fx)
+    ctx.inverse_transform_rns(work, work, libs, batch)
+    ctx.forward_transform_rns(work, work, [libs[0]], 1)    # one polynomial of it
+    got = work.to_host()
+    assert np.array_equal(got[:n], oracle.forward(x[:n], oras[0]))
+    assert np.array_equal(got[n:], x[n:])
+    # a RECORDED operation on the same vector between two sliced transforms:
+    # it is launched (on the context's stream) when the next call fetches its
+    # pointers, and must find every slice finished
+    ctx.inverse_transform_rns(work, work, [libs[0]], 1)
+    ones = ctx.from_host(np.ones(x.size, np.uint64))
+    f0 = ctx.fused_products
+    ctx.forward_transform_rns(data, work, libs, batch)     # slices in flight
+    ctx.elemmul(work, ones, work, params.Q61)              # recorded; identity
+    ctx.inverse_transform_rns(work, work, libs, batch)     # launches it first
+    assert np.array_equal(work.to_host(), x)
+    assert ctx.fused_products == f0
+    ones.destroy()
+    # transfers: a download behind the slices, an upload in front of them
+    pinned, back = vk.host_alloc(x.size), vk.host_alloc(x.size)
+    pinned.array[:] = x
+    ctx.forward_transform_rns(data, work, libs, batch)
+    work.download(back)
+    ctx.sync()
+    assert np.array_equal(back.array, fx)
+    work.upload(pinned)
+    ctx.forward_transform_rns(work, work, libs, batch)
+    ctx.inverse_transform_rns(work, work, libs, batch)
+    work.download(back)
+    ctx.sync()
+    assert np.array_equal(back.array, x)
+    for v in (data, work, other):
+        v.destroy()
+    for t in tps:
+        t.destroy()
+    pinned.free(), back.free()

@@ -154,6 +154,10 @@ void launch_ntt_cols_tma(struct vkhel_ctx *ctx, bool apx, const u64 *src,
 		u64 *dst, const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned limbs_total, unsigned limb0);
 
+/* kernels_ntt.cu: make the context's stream wait for the slices a sliced
+ * transform has left on the auxiliary stream (no-op when there are none) */
+void ntt_split_join(struct vkhel_ctx *ctx);
+
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */
 void defer_flush(struct vkhel_ctx *ctx);

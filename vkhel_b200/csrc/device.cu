@@ -150,6 +150,7 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	cudaStream_t stream = (cudaStream_t) dev->stream;
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_d2h));
+	CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_aux));
 	CUDA_CHECK(cudaStreamSynchronize(stream));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_d2h));

@@ -1857,6 +1857,41 @@ static size_t slice_bytes_setting(bool by_limb, bool *forced) {
 	return by_limb ? (size_t) VKHEL_DEFAULT_SLICE_MIB << 20 : 0;
 }
 
+void ntt_split_join(struct vkhel_ctx *ctx) {
+	if (!ctx->dev.split_active) {
+		return;
+	}
+	ctx->dev.split_active = 0;
+	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_aux;
+	CUDA_CHECK(cudaEventRecord(ev, (cudaStream_t) ctx->dev.stream_aux));
+	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(ctx), ev, 0));
+}
+
+/* $VKHEL_LAZY_JOIN=0: join the two streams at the end of every sliced
+ * transform (the round-1 behaviour) */
+static bool lazy_join() {
+	static int v = -1;
+	if (v < 0) {
+		const char *env = getenv("VKHEL_LAZY_JOIN");
+		v = !(env && !strcmp(env, "0"));
+	}
+	return v;
+}
+
+/* $VKHEL_SPLIT_SMALL_MIB (default 8): an RNS batch that fits in L2 is still cut
+ * in two limb slices, one per stream, when it holds at least this much: the
+ * launch and drain of one slice's kernels overlap the other slice's
+ * butterflies (0 = never) */
+static size_t split_small_bytes() {
+	static double mib = -1;
+	if (mib < 0) {
+		const char *env = getenv("VKHEL_SPLIT_SMALL_MIB");
+		mib = env && *env ? atof(env) : 8;
+	}
+	return (size_t) (mib * 1048576.0);
+}
+
 static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		const u64 *src, u64 *dst, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n) {
@@ -1866,33 +1901,53 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 	const fast_plan pl = plan_fast(log2n);
 	const size_t poly_bytes = sizeof(u64) << log2n;
 	const size_t total = polys * poly_bytes;
-	if (!slice || !pl.kcol || pl.lead || total < 3 * slice
-			|| (log2n >= 9 && log2n <= single_max_log2n())
-			|| (!forced && total <= ctx->dev.l2_bytes)) {
-		return false;   /* single pass, or the batch fits in L2 anyway */
-	}
 	const uint64_t batch = polys / limbs;
 	/* units: limbs (all batch entries of each) or, for one modulus, batch
 	 * entries */
 	const uint64_t units = by_limb ? limbs : batch;
 	const size_t unit_bytes = (by_limb ? batch : 1) * poly_bytes;
-	uint64_t per = slice / unit_bytes;
-	if (per < 1) {
-		per = 1;
+	uint64_t per = 0;
+	if (!pl.kcol || pl.lead || (log2n >= 9 && log2n <= single_max_log2n())) {
+		return false;   /* one pass, or a leading generic pass */
 	}
-	if (!by_limb && per < 16 && per < units) {
-		per = 16 < units ? 16 : units;   /* keep the twiddle sharing of the row pass */
+	if (slice && total >= 3 * slice
+			&& (forced || total > ctx->dev.l2_bytes)) {
+		/* larger than L2: slices small enough to stay in it between passes */
+		per = slice / unit_bytes;
+		if (per < 1) {
+			per = 1;
+		}
+		if (!by_limb && per < 16 && per < units) {
+			per = 16 < units ? 16 : units;   /* keep the twiddle sharing of the row pass */
+		}
+	} else if (!forced && by_limb && units >= 2 && lazy_join()
+			&& split_small_bytes() && total >= split_small_bytes()) {
+		/* fits in L2: two halves, one per stream */
+		per = (units + 1) / 2;
 	}
-	const uint64_t nslices = (units + per - 1) / per;
+	const uint64_t nslices = per ? (units + per - 1) / per : 0;
 	if (nslices < 2) {
 		return false;
 	}
 	cudaStream_t main_stream = ctx_stream(ctx);
 	cudaStream_t aux = (cudaStream_t) ctx->dev.stream_aux;
 	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_aux;
-	/* fork: the auxiliary stream continues from here */
-	CUDA_CHECK(cudaEventRecord(ev, main_stream));
-	CUDA_CHECK(cudaStreamWaitEvent(aux, ev, 0));
+	struct device_ctx *dev = &ctx->dev;
+	const bool continues = dev->split_active && dev->split_dst == (const void *) dst
+		&& dev->split_bytes == total && dev->split_per == per
+		&& dev->split_units == units && dev->split_by_limb == (int) by_limb
+		&& dev->split_log2n == log2n;
+	if (!continues) {
+		/* (join what another partition has left,) fork: the auxiliary
+		 * stream continues from here */
+		ntt_split_join(ctx);
+		CUDA_CHECK(cudaEventRecord(ev, main_stream));
+		CUDA_CHECK(cudaStreamWaitEvent(aux, ev, 0));
+	}
+	/* else: slice i follows slice i of the transform before it on the same
+	 * stream -- it reads and writes only what that one wrote (or reads a
+	 * vector no pending slice writes) */
+	dev->split_active = 0;
 	for (uint64_t i = 0; i < nslices; i++) {
 		const uint64_t u0 = i * per;
 		const uint64_t cnt = units - u0 < per ? units - u0 : per;
@@ -1907,9 +1962,21 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		}
 	}
 	ctx->dev.launch_stream = NULL;
-	/* join */
-	CUDA_CHECK(cudaEventRecord(ev, aux));
-	CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
+	if (lazy_join()) {
+		/* the join is left to whoever needs the context's stream next
+		 * (defer_flush -> ntt_split_join), or to nobody if the next call is
+		 * the same partition of the same vector again */
+		dev->split_active = 1;
+		dev->split_dst = dst;
+		dev->split_bytes = total;
+		dev->split_per = per;
+		dev->split_units = units;
+		dev->split_by_limb = by_limb;
+		dev->split_log2n = log2n;
+	} else {
+		CUDA_CHECK(cudaEventRecord(ev, aux));
+		CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
+	}
 	return true;
 }
 
@@ -1927,6 +1994,13 @@ void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 					log2n)) {
 			return;
 		}
+	}
+	/* not a sliced transform: slices a previous one left on the auxiliary
+	 * stream (the caller may have held the join back, sliced_operands in
+	 * vector.cu) are joined before anything is launched */
+	ntt_split_join(ctx);
+	if (!strict && log2n >= 3 && !force_generic) {
+		const bool apx = use_approx(q_max, log2n);
 		run_fast_any(ctx, inverse, apx, src, dst, descs, limbs, polys, log2n,
 				0, 0);
 		return;

@@ -44,12 +44,14 @@ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) {
  * so that ptxas emits the ten (nine) multiplies as IMAD / IMAD.WIDE / IMAD.HI
  * with their accumulators chained and no separate add, negate or move
  * (tools/bfly_bench.cu v19: +7 % butterfly rate over the C expression). */
-#ifndef SHOUP_SPARSE60
-#define SHOUP_SPARSE60 0
-#endif
+/* (Measured and dropped, profiles/r02_variants_a.txt: for moduli just below a
+ * power of two the high word of 2^64 - q is 2^32 - 2^s, so h0*n1 is a shift and
+ * a subtraction instead of a multiply -- one fmaheavy slot of 16 fewer per
+ * butterfly, and the transform 5-7 % SLOWER: the funnel shift runs at 49.5
+ * per clock per SM and three-input additions with two carries at a third of
+ * the IADD3 rate, vkhel_ctx_probe_int_peaks.) */
 template <bool APPROX>
-__device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq,
-		unsigned zr = 0) {
+__device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq) {
 	const unsigned y0 = (unsigned) y, y1 = (unsigned) (y >> 32);
 	const unsigned w0 = (unsigned) w, w1 = (unsigned) (w >> 32);
 	const unsigned p0 = (unsigned) wp, p1 = (unsigned) (wp >> 32);
@@ -71,20 +73,12 @@ __device__ __forceinline__ u64 shoup_chain(u64 y, u64 w, u64 wp, u64 nq,
 		    "madc.hi.u32 %1, h0, %8, %1;\n\t"
 		    "mad.lo.u32 %1, %2, %5, %1;\n\t"       /* t.hi += y0*w1 */
 		    "mad.lo.u32 %1, %3, %4, %1;\n\t"       /* t.hi += y1*w0 */
-#if SHOUP_SPARSE60
-		    /* experiment, moduli in (2^60 - 2^32, 2^60) only: the high word
-		     * of 2^64 - q is 0xF0000000, so h0*n1 = -(h0 << 28) mod 2^32 */
-		    "shf.l.clamp.b32 r0, 0, h0, 28;\n\t"
-		    "sub.u32 %1, %1, r0;\n\t"
-		    "add.u32 %1, %1, %10;\n\t"
-#else
 		    "mad.lo.u32 %1, h0, %9, %1;\n\t"       /* t.hi += h0*n1 */
-#endif
 		    "mad.lo.u32 %1, h1, %8, %1;\n\t"       /* t.hi += h1*n0 */
 		    "}"
 		    : "=&r"(t0), "=&r"(t1)
 		    : "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0),
-		      "r"(n1), "r"(zr));
+		      "r"(n1));
 	} else {
 		asm("{\n\t"
 		    ".reg .u32 r0, h0, h1;\n\t"
@@ -147,9 +141,8 @@ __device__ __forceinline__ u64 mulhi64_approx(u64 a, u64 b) {
 /* Shoup product with the approximate quotient: the quotient estimate is at
  * most one further below the true one, so the result is y*w mod q plus
  * {0, q, 2q}: in [0,3q) for ANY 64-bit y.  Needs 3q < 2^64. */
-__device__ __forceinline__ u64 shoup_lazy3(u64 y, u64 w, u64 wp, u64 q,
-		unsigned zr = 0) {
-	return shoup_chain<true>(y, w, wp, 0 - q, zr);
+__device__ __forceinline__ u64 shoup_lazy3(u64 y, u64 w, u64 wp, u64 q) {
+	return shoup_chain<true>(y, w, wp, 0 - q);
 }
 
 __device__ __forceinline__ u64 shoup_canon(u64 y, u64 w, u64 wp, u64 q) {
@@ -210,7 +203,7 @@ __device__ __forceinline__ void gs_lazy(u64 &x, u64 &y, u64 w, u64 wp,
 __device__ __forceinline__ void ct_lazy3(u64 &x, u64 &y, u64 w, u64 wp,
 		u64 q, u64 threeq, u64 zr = 0) {
 	const u64 xr = csub(x, threeq);
-	const u64 t = shoup_lazy3(y, w, wp, q, (unsigned) zr);
+	const u64 t = shoup_lazy3(y, w, wp, q);
 	x = xr + t + zr;
 	y = xr - t + threeq;
 }
@@ -220,7 +213,7 @@ __device__ __forceinline__ void gs_lazy3(u64 &x, u64 &y, u64 w, u64 wp,
 	const u64 s = x + y + zr;
 	const u64 d = x - y + threeq;
 	x = csub(s, threeq);
-	y = shoup_lazy3(d, w, wp, q, (unsigned) zr);
+	y = shoup_lazy3(d, w, wp, q);
 }
 
 /* ---- strict butterflies: every value canonical (2^62 <= q < 2^63) ---------- */

@@ -246,7 +246,16 @@ static void readahead_advance(struct vkhel_vector *vec) {
 }
 
 void defer_flush(struct vkhel_ctx *ctx) {
+	/* everything that is about to use the context's stream comes through
+	 * here: slices still on the auxiliary stream are joined first */
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	/* (a batched transform that may continue the slices holds the join back
+	 * while it fetches its pointers -- but not if recorded work is launched
+	 * here, which goes to the context's stream and may touch the same vector) */
+	if (!ctx->dev.split_hold
+			|| (dq && (!dq->items.empty() || dq->mul.active))) {
+		ntt_split_join(ctx);
+	}
 	if (!dq) {
 		return;
 	}
@@ -1029,6 +1038,20 @@ extern "C" void vkhel_vector_inverse_transform(
 	DBG_VEC("result", result);
 }
 
+/* Device pointers for a batched transform that may continue a sliced
+ * transform slice by slice (device.h, split_*): fetching them does not join
+ * the auxiliary stream -- unless a transfer of one of the vectors is pending,
+ * which only the context's stream would wait for.  launch_ntt joins if the new
+ * transform does not fit the slices that are in flight. */
+static void sliced_operands(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, const u64 **src, u64 **dst) {
+	struct vkhel_ctx *ctx = result->ctx;
+	ctx->dev.split_hold = !operand->xfer_pending && !result->xfer_pending;
+	*src = dev_u64(operand);
+	*dst = dev_u64(result);
+	ctx->dev.split_hold = 0;
+}
+
 static const limb_desc *rns_prepare(const char *what,
 		const struct vkhel_vector *operand, const struct vkhel_vector *result,
 		struct vkhel_ntt_tables *const *ntt, uint64_t limbs, uint64_t batch,
@@ -1054,7 +1077,10 @@ extern "C" void vkhel_vector_forward_transform_rns(
 	if (ntt[0]->n < 2 || batch == 0) {
 		return;
 	}
-	launch_ntt(result->ctx, false, dev_u64(operand), dev_u64(result), descs,
+	const u64 *src;
+	u64 *dst;
+	sliced_operands(operand, result, &src, &dst);
+	launch_ntt(result->ctx, false, src, dst, descs,
 			limbs, limbs * batch, (unsigned) ntt[0]->log2n, q_max);
 }
 
@@ -1069,7 +1095,10 @@ extern "C" void vkhel_vector_inverse_transform_rns(
 	if (batch == 0) {
 		return;
 	}
-	launch_ntt(result->ctx, true, dev_u64(operand), dev_u64(result), descs,
+	const u64 *src;
+	u64 *dst;
+	sliced_operands(operand, result, &src, &dst);
+	launch_ntt(result->ctx, true, src, dst, descs,
 			limbs, limbs * batch, (unsigned) ntt[0]->log2n, q_max);
 }
 
