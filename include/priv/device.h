@@ -39,6 +39,10 @@ struct device_ctx {
 	void *ev_scratch;    /* cudaEvent_t used to fork from the compute stream */
 	void *stream_aux;    /* second compute stream for sliced transforms */
 	void *ev_aux;        /* fork/join event of the sliced transforms */
+	/* further compute streams for sliced transforms ($VKHEL_SLICE_STREAMS > 2),
+	 * created on first use, with their join events */
+	void *stream_more[2];
+	void *ev_more[2];
 	void *launch_stream; /* non-NULL while kernels go to stream_aux */
 	/* Lazy join of a sliced transform (kernels_ntt.cu, run_fast_sliced): the
 	 * odd slices of the last sliced transform are still un-joined on

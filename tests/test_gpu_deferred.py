@@ -415,3 +415,128 @@ def test_elemfma_followed_by_inverse_is_fused(ctx, log2n, mult):
     for v in (a, b, c):
         v.destroy()
     t.destroy()
+
+
+# ---- recorded whole products (n <= 2^11) ----------------------------------------------------------
+def product_quad(ctx, a, b, c, t, swap=False):
+    """the reference's four calls (examples/example.c:18-60)"""
+    ctx.forward_transform(a, a, t.lib)
+    ctx.forward_transform(b, b, t.lib)
+    if swap:
+        ctx.elemmul(b, a, c, t.q)
+    else:
+        ctx.elemmul(a, b, c, t.q)
+    ctx.inverse_transform(c, c, t.lib)
+
+
+@pytest.mark.parametrize("log2n,count", [(3, 5), (4, 3), (6, 9), (8, 40),
+                                         (9, 7), (10, 33), (11, 6)])
+def test_loop_of_small_products_is_one_launch(ctx, log2n, count):
+    """A loop of four-call products over separate vector triples at n <= 2^11:
+    every product is recorded as a unit and the whole loop goes out as ONE
+    launch (kernels_ntt_small.cu); products and the (still observable) forward
+    transforms equal the oracle's."""
+    n, q = 1 << log2n, params.P0
+    t = Tables(n, q)
+    rng = np.random.default_rng(7000 + log2n)
+    xs = [rand_mod(rng, n, q) for _ in range(count)]
+    ys = [rand_mod(rng, n, q) for _ in range(count)]
+    va = [ctx.from_host(x) for x in xs]
+    vb = [ctx.from_host(y) for y in ys]
+    vc = [ctx.vector(n) for _ in range(count)]
+    ctx.sync()
+    l0, f0 = ctx.launch_count, ctx.fused_products
+    for i in range(count):
+        product_quad(ctx, va[i], vb[i], vc[i], t, swap=bool(i & 1))
+    assert ctx.launch_count_noflush == l0          # nothing launched yet
+    ctx.flush()
+    assert ctx.launch_count == l0 + 1
+    assert ctx.fused_products == f0 + count
+    for i in range(count):
+        fx, fy = oracle.forward(xs[i], t.ora), oracle.forward(ys[i], t.ora)
+        assert np.array_equal(vc[i].to_host(), product_oracle(fx, fy, t)), i
+        assert np.array_equal(va[i].to_host(), fx), i
+        assert np.array_equal(vb[i].to_host(), fy), i
+    for v in va + vb + vc:
+        v.destroy()
+    t.destroy()
+
+
+def test_small_products_out_of_place_reused_vectors_and_interruptions(ctx):
+    n, q = 1 << 10, params.P0
+    t = Tables(n, q)
+    t2 = Tables(n, params.Q61)
+    rng = np.random.default_rng(7100)
+    x, y, z = (rand_mod(rng, n, q) for _ in range(3))
+    fx, fy, fz = (oracle.forward(v, t.ora) for v in (x, y, z))
+    a, b, w = ctx.from_host(x), ctx.from_host(y), ctx.from_host(z)
+    fa, fb, c, c2 = (ctx.vector(n) for _ in range(4))
+    # forward transforms out of place: the sources stay what they were
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    ctx.inverse_transform(c, c, t.lib)
+    # a recorded transform of an unrelated vector shares the record
+    ctx.forward_transform(w, w, t.lib)
+    # the same operands again, into another result: depends on nothing recorded
+    # that it overwrites, but re-transforms fa/fb -> launched in order
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c2, q)
+    ctx.inverse_transform(c2, c2, t.lib)
+    want = product_oracle(fx, fy, t)
+    assert np.array_equal(c.to_host(), want)
+    assert np.array_equal(c2.to_host(), want)
+    assert np.array_equal(a.to_host(), x) and np.array_equal(fa.to_host(), fx)
+    assert np.array_equal(w.to_host(), fz)
+    # interrupted: the product is read before any inverse transform
+    f0 = ctx.fused_products
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    assert np.array_equal(c.to_host(), oracle.elemmul(fx, fy, q))
+    # ... the inverse goes elsewhere, or uses other tables
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    ctx.inverse_transform(c, c2, t.lib)
+    assert np.array_equal(c2.to_host(), want)
+    assert np.array_equal(c.to_host(), oracle.elemmul(fx, fy, q))
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    ctx.inverse_transform(c, c, t2.lib)
+    assert np.array_equal(c.to_host(),
+                          oracle.inverse(oracle.elemmul(fx, fy, q), t2.ora))
+    # ... another transform is recorded, or an operand is destroyed, in between
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    ctx.forward_transform(w, w, t.lib)          # w = forward(forward(z))
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), want)
+    assert np.array_equal(w.to_host(), oracle.forward(fz, t.ora))
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(b, fb, t.lib)
+    ctx.elemmul(fa, fb, c, q)
+    fb.destroy()
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), want)
+    assert ctx.fused_products == f0
+    # squaring and in-place products are not whole-product candidates
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.elemmul(fa, fa, c, q)
+    ctx.inverse_transform(c, c, t.lib)
+    assert np.array_equal(c.to_host(), product_oracle(fx, fx, t))
+    # tables destroyed while a recorded product still needs them
+    ctx.forward_transform(a, fa, t.lib)
+    ctx.forward_transform(w, w, t.lib)
+    ctx.elemmul(fa, w, c, q)
+    ctx.inverse_transform(c, c, t.lib)
+    fw = oracle.forward(oracle.forward(fz, t.ora), t.ora)
+    t.destroy()
+    t3 = Tables(n, q)
+    assert np.array_equal(c.to_host(), product_oracle(fx, fw, t3))
+    for v in (a, b, w, fa, c, c2):
+        v.destroy()
+    t2.destroy(), t3.destroy()

@@ -158,6 +158,21 @@ void launch_ntt_cols_tma(struct vkhel_ctx *ctx, bool apx, const u64 *src,
  * transform has left on the auxiliary stream (no-op when there are none) */
 void ntt_split_join(struct vkhel_ctx *ctx);
 
+/* kernels_ntt_small.cu: whole products c = INTT(NTT(a) (*) NTT(b)) of small
+ * polynomials (8 <= n <= 2^11), one CTA each, `count` of them in one launch;
+ * the forward transforms are stored too (a_dst, b_dst).  Pointer table in
+ * device memory (`tab`) or, for at most 4 products, in host memory
+ * (`host_tab`, travels in the kernel parameters). */
+#define SMALL_PRODUCT_MAX_LOG2N 11
+struct small_product {
+	const u64 *a_src, *b_src;
+	u64 *a_dst, *b_dst, *c;
+};
+bool ntt_small_product_supported(unsigned log2n, uint64_t q);
+void launch_ntt_small_products(struct vkhel_ctx *ctx, const small_product *tab,
+		const small_product *host_tab, unsigned count, const limb_desc *desc,
+		unsigned log2n, uint64_t q);
+
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */
 void defer_flush(struct vkhel_ctx *ctx);

@@ -155,6 +155,13 @@ extern "C" void device_ctx_finish(struct device_ctx *dev) {
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_h2d));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_d2h));
 	CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_aux));
+	for (int i = 0; i < 2; i++) {
+		if (dev->stream_more[i]) {
+			CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) dev->stream_more[i]));
+			CUDA_CHECK(cudaStreamDestroy((cudaStream_t) dev->stream_more[i]));
+			CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_more[i]));
+		}
+	}
 	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_scratch));
 	CUDA_CHECK(cudaEventDestroy((cudaEvent_t) dev->ev_aux));
 	for (int i = 0; i < VKHEL_FORK_EVENTS; i++) {

@@ -1857,15 +1857,52 @@ static size_t slice_bytes_setting(bool by_limb, bool *forced) {
 	return by_limb ? (size_t) VKHEL_DEFAULT_SLICE_MIB << 20 : 0;
 }
 
+/* streams the slices of a transform alternate between: the context's, the
+ * auxiliary one, and up to two more ($VKHEL_SLICE_STREAMS, default 2) */
+static int slice_streams() {
+	static int v = -1;
+	if (v < 0) {
+		const char *env = getenv("VKHEL_SLICE_STREAMS");
+		v = env && *env ? atoi(env) : 2;
+		v = v < 2 ? 2 : v > 4 ? 4 : v;
+	}
+	return v;
+}
+
+/* stream number k (0 = the context's stream) and the event that joins it */
+static cudaStream_t slice_stream(struct vkhel_ctx *ctx, int k, cudaEvent_t *ev) {
+	struct device_ctx *dev = &ctx->dev;
+	if (k == 0) {
+		return ctx_stream(ctx);
+	}
+	if (k == 1) {
+		*ev = (cudaEvent_t) dev->ev_aux;
+		return (cudaStream_t) dev->stream_aux;
+	}
+	if (!dev->stream_more[k - 2]) {
+		cudaStream_t st;
+		cudaEvent_t e;
+		CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		dev->stream_more[k - 2] = st;
+		dev->ev_more[k - 2] = e;
+	}
+	*ev = (cudaEvent_t) dev->ev_more[k - 2];
+	return (cudaStream_t) dev->stream_more[k - 2];
+}
+
 void ntt_split_join(struct vkhel_ctx *ctx) {
 	if (!ctx->dev.split_active) {
 		return;
 	}
 	ctx->dev.split_active = 0;
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
-	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_aux;
-	CUDA_CHECK(cudaEventRecord(ev, (cudaStream_t) ctx->dev.stream_aux));
-	CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(ctx), ev, 0));
+	for (int k = 1; k < slice_streams(); k++) {
+		cudaEvent_t ev;
+		cudaStream_t st = slice_stream(ctx, k, &ev);
+		CUDA_CHECK(cudaEventRecord(ev, st));
+		CUDA_CHECK(cudaStreamWaitEvent(ctx_stream(ctx), ev, 0));
+	}
 }
 
 /* $VKHEL_LAZY_JOIN=0: join the two streams at the end of every sliced
@@ -1930,8 +1967,7 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		return false;
 	}
 	cudaStream_t main_stream = ctx_stream(ctx);
-	cudaStream_t aux = (cudaStream_t) ctx->dev.stream_aux;
-	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_aux;
+	cudaEvent_t ev = (cudaEvent_t) ctx->dev.ev_scratch;   /* fork */
 	struct device_ctx *dev = &ctx->dev;
 	const bool continues = dev->split_active && dev->split_dst == (const void *) dst
 		&& dev->split_bytes == total && dev->split_per == per
@@ -1942,7 +1978,10 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		 * stream continues from here */
 		ntt_split_join(ctx);
 		CUDA_CHECK(cudaEventRecord(ev, main_stream));
-		CUDA_CHECK(cudaStreamWaitEvent(aux, ev, 0));
+		for (int k = 1; k < slice_streams(); k++) {
+			cudaEvent_t unused;
+			CUDA_CHECK(cudaStreamWaitEvent(slice_stream(ctx, k, &unused), ev, 0));
+		}
 	}
 	/* else: slice i follows slice i of the transform before it on the same
 	 * stream -- it reads and writes only what that one wrote (or reads a
@@ -1951,7 +1990,12 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 	for (uint64_t i = 0; i < nslices; i++) {
 		const uint64_t u0 = i * per;
 		const uint64_t cnt = units - u0 < per ? units - u0 : per;
-		ctx->dev.launch_stream = (i & 1) ? (void *) aux : NULL;
+		{
+			cudaEvent_t unused;
+			const int k = (int) (i % (uint64_t) slice_streams());
+			ctx->dev.launch_stream = k ? (void *) slice_stream(ctx, k, &unused)
+				: NULL;
+		}
 		if (by_limb) {
 			run_fast_any(ctx, inverse, apx, src, dst, descs + u0, cnt,
 					cnt * batch, log2n, (unsigned) limbs, (unsigned) u0);
@@ -1974,8 +2018,8 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		dev->split_by_limb = by_limb;
 		dev->split_log2n = log2n;
 	} else {
-		CUDA_CHECK(cudaEventRecord(ev, aux));
-		CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
+		dev->split_active = 1;
+		ntt_split_join(ctx);
 	}
 	return true;
 }

@@ -63,13 +63,28 @@ struct defer_item {
 struct pending_product {
 	bool active;
 	bool fma;             /* a*multiplier + b instead of a*b */
+	/* the two forward transforms that produced a and b are held back with it
+	 * (defer_queue::triple): a candidate for a recorded whole product */
+	bool with_forwards;
 	const struct vkhel_vector *a, *b;
 	struct vkhel_vector *result;
 	uint64_t mod, multiplier;
 };
 
+/* most whole products recorded for one launch (40 bytes of pointers each) */
+#define PRODUCTS_MAX 1024
+
 struct defer_queue {
 	pending_product mul;
+	/* ---- recorded whole products (small n, see "recorded whole products") ---- */
+	struct {
+		bool active;
+		defer_item fa, fb;                 /* the forward transforms of a and b */
+		struct vkhel_ntt_tables *ntt;
+	} triple;
+	std::vector<small_product> products;   /* complete four-call products */
+	std::vector<struct vkhel_vector *> product_results;
+	struct vkhel_ntt_tables *product_tables;
 	bool inverse;
 	uint64_t log2n;
 	std::vector<struct vkhel_ntt_tables *> tables;   /* distinct, <= DEFER_TABLES */
@@ -89,6 +104,9 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 		enter(ctx);
 		defer_queue *dq = new defer_queue();
 		dq->mul.active = false;
+		dq->mul.with_forwards = false;
+		dq->triple.active = false;
+		dq->product_tables = NULL;
 		dq->inverse = false;
 		dq->log2n = 0;
 		dq->half = 0;
@@ -143,6 +161,50 @@ static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 }
 
 static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq);
+
+/* ---- recorded whole products -----------------------------------------------------------
+ * For n <= 2^11 a transform is one small kernel, and the reference's product --
+ * forward(a), forward(b), elemmul(a, b, c), inverse(c) in place
+ * (examples/example.c:18-60) -- is bound by its launches even with the product
+ * fused into the inverse transform (three launches).  The four calls are
+ * therefore recognised as a unit: elemmul takes the two forward transforms
+ * that produced its operands back out of the record (`triple`), and the
+ * matching inverse transform turns the three into ONE recorded whole product.
+ * Recorded products are independent of each other and of the recorded
+ * transforms (the same read/write sets guard them), so a loop of products goes
+ * out as one launch of ntt_small_product_kernel, one CTA per product
+ * (kernels_ntt_small.cu); the forward results are stored as well, a and b stay
+ * observable.  Anything that is not the matching inverse launches the held
+ * calls one by one, in order. */
+static void launch_recorded_products(struct vkhel_ctx *ctx, defer_queue *dq) {
+	const size_t count = dq->products.size();
+	if (!count) {
+		return;
+	}
+	struct vkhel_ntt_tables *ntt = dq->product_tables;
+	const limb_desc *desc = ntt_tables_device_desc(ctx, ntt);
+	if (count <= 4) {
+		launch_ntt_small_products(ctx, NULL, dq->products.data(),
+				(unsigned) count, desc, (unsigned) ntt->log2n, ntt->q);
+	} else {
+		const size_t bytes = count * sizeof(small_product);
+		const int h = dq->half;
+		dq->half ^= 1;
+		CUDA_CHECK(cudaEventSynchronize(dq->staged[h]));
+		memcpy(dq->stage[h], dq->products.data(), bytes);
+		small_product *tab = (small_product *) device_alloc(ctx, bytes);
+		CUDA_CHECK(cudaMemcpyAsync(tab, dq->stage[h], bytes,
+					cudaMemcpyHostToDevice, ctx_stream(ctx)));
+		CUDA_CHECK(cudaEventRecord(dq->staged[h], ctx_stream(ctx)));
+		launch_ntt_small_products(ctx, tab, NULL, (unsigned) count, desc,
+				(unsigned) ntt->log2n, ntt->q);
+		device_free(ctx, tab);   /* stream-ordered: after the kernel */
+	}
+	ctx->dev.deferred_batches++;
+	dq->products.clear();
+	dq->product_results.clear();
+	dq->product_tables = NULL;
+}
 
 /* ---- read-ahead for map() ------------------------------------------------------------
  * The reference reads results by mapping one vector after the other
@@ -253,16 +315,18 @@ void defer_flush(struct vkhel_ctx *ctx) {
 	 * while it fetches its pointers -- but not if recorded work is launched
 	 * here, which goes to the context's stream and may touch the same vector) */
 	if (!ctx->dev.split_hold
-			|| (dq && (!dq->items.empty() || dq->mul.active))) {
+			|| (dq && (!dq->items.empty() || !dq->products.empty()
+					|| dq->mul.active))) {
 		ntt_split_join(ctx);
 	}
 	if (!dq) {
 		return;
 	}
-	if (dq->items.empty()) {
-		/* transforms and a product are never recorded at the same time: each
-		 * launches the other kind when it is recorded */
-		flush_product(ctx, dq);
+	if (dq->items.empty() && dq->products.empty()) {
+		flush_product(ctx, dq);   /* (with its forward transforms, if held) */
+		dq->tables.clear();
+		dq->reads.clear();
+		dq->writes.clear();
 		return;
 	}
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
@@ -271,10 +335,23 @@ void defer_flush(struct vkhel_ctx *ctx) {
 	/* the vectors a loop of maps is likely to ask for next (read-ahead) */
 	readahead_list *ra = readahead_get(ctx);
 	ra->results.clear();
-	if (count > 1) {
+	if (count + dq->product_results.size() > 1) {
 		for (const defer_item &it : dq->items) {
 			ra->results.push_back(it.result);
 		}
+		for (struct vkhel_vector *v : dq->product_results) {
+			ra->results.push_back(v);
+		}
+	}
+	/* recorded transforms, recorded products and a held product are
+	 * independent of each other (the read/write sets): any order will do */
+	launch_recorded_products(ctx, dq);
+	flush_product(ctx, dq);
+	if (!count) {
+		dq->tables.clear();
+		dq->reads.clear();
+		dq->writes.clear();
+		return;
 	}
 	/* An indirect batch costs a pointer-table copy on top of its launches;
 	 * a record that short is cheaper launched transform by transform:
@@ -298,7 +375,7 @@ void defer_flush(struct vkhel_ctx *ctx) {
 		for (const defer_item &it : dq->items) {
 			by_table[it.table].push_back(it.ptrs);
 		}
-		bool rectangular = true;
+		bool rectangular = !by_table[0].empty();
 		for (size_t t = 1; t < ntab; t++) {
 			rectangular = rectangular
 				&& by_table[t].size() == by_table[0].size();
@@ -323,6 +400,9 @@ void defer_flush(struct vkhel_ctx *ctx) {
 		} else {
 			for (size_t t = 0; t < ntab; t++) {
 				struct vkhel_ntt_tables *ntt = dq->tables[t];
+				if (by_table[t].empty()) {
+					continue;   /* its transforms became part of a product */
+				}
 				if (by_table[t].size() == 1) {
 					launch_ntt(ctx, dq->inverse, by_table[t][0].src,
 							by_table[t][0].dst,
@@ -345,6 +425,10 @@ void defer_flush_tables(struct vkhel_ctx *ctx,
 		const struct vkhel_ntt_tables *ntt) {
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
 	if (!dq) {
+		return;
+	}
+	if (dq->product_tables == ntt || (dq->triple.active && dq->triple.ntt == ntt)) {
+		defer_flush(ctx);
 		return;
 	}
 	for (const struct vkhel_ntt_tables *t : dq->tables) {
@@ -389,13 +473,14 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 	flush_product(ctx, dq);
 	const void *rd = operand->device.ptr, *wr = result->device.ptr;
 	unsigned table = 0;
-	if (!dq->items.empty()) {
+	if (!dq->items.empty() || !dq->products.empty()) {
 		while (table < dq->tables.size() && dq->tables[table] != ntt) {
 			table++;
 		}
-		if (dq->inverse != inverse || dq->log2n != ntt->log2n
-				|| dq->items.size() >= DEFER_MAX
-				|| table >= DEFER_TABLES
+		const bool other_batch = !dq->items.empty()
+			&& (dq->inverse != inverse || dq->log2n != ntt->log2n
+					|| dq->items.size() >= DEFER_MAX);
+		if (other_batch || table >= DEFER_TABLES
 				|| dq->writes.count(rd) || dq->writes.count(wr)
 				|| dq->reads.count(wr)) {
 			/* different batch, or this transform depends on a recorded one
@@ -448,6 +533,19 @@ static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq) {
 	}
 	dq->mul.active = false;
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+	if (dq->mul.with_forwards) {
+		/* the product did not become a recorded whole product: its two
+		 * forward transforms, taken out of the record, go first */
+		dq->mul.with_forwards = false;
+		dq->triple.active = false;
+		struct vkhel_ntt_tables *ntt = dq->triple.ntt;
+		const defer_item *fwd[2] = { &dq->triple.fa, &dq->triple.fb };
+		for (const defer_item *it : fwd) {
+			launch_ntt(ctx, false, it->ptrs.src, it->ptrs.dst,
+					ntt_tables_device_desc(ctx, ntt), 1, 1,
+					(unsigned) ntt->log2n, ntt->q);
+		}
+	}
 	const pending_product &m = dq->mul;
 	if (m.fma) {
 		launch_elemfma(ctx, dev_u64_nodefer(m.a), dev_u64_nodefer(m.b),
@@ -469,6 +567,30 @@ static bool fuse_product_into_inverse(const struct vkhel_vector *operand,
 		return false;
 	}
 	const pending_product m = dq->mul;
+	if (m.with_forwards) {
+		if (operand == result && result == m.result && ntt == dq->triple.ntt) {
+			/* forward, forward, elemmul, inverse: one recorded whole product */
+			small_product sp;
+			sp.a_src = dq->triple.fa.ptrs.src;
+			sp.a_dst = dq->triple.fa.ptrs.dst;
+			sp.b_src = dq->triple.fb.ptrs.src;
+			sp.b_dst = dq->triple.fb.ptrs.dst;
+			sp.c = dev_u64_nodefer(result);
+			dq->products.push_back(sp);
+			dq->product_results.push_back(result);
+			dq->product_tables = ntt;
+			dq->mul.active = false;
+			dq->mul.with_forwards = false;
+			dq->triple.active = false;
+			ctx->dev.fused_products++;
+			ctx->dev.deferred_transforms += 3;
+			if (dq->products.size() >= PRODUCTS_MAX) {
+				defer_flush(ctx);
+			}
+			return true;
+		}
+		return false;   /* the caller's path launches the three held calls */
+	}
 	if (operand != result || result != m.result || m.mod != ntt->q
 			|| result->length != ntt->n || !dq->items.empty()) {
 		return false;   /* the caller's path launches the product first */
@@ -836,9 +958,47 @@ static bool record_pointwise(bool fma, const struct vkhel_vector *a,
 			|| mod >= (1ull << 62)) {
 		return false;
 	}
-	defer_flush(result->ctx);   /* what was recorded so far goes first */
 	defer_queue *dq = defer_get(result->ctx);
+	/* the product of two vectors whose forward transforms are the last two
+	 * recorded calls: hold all three for the inverse transform that would
+	 * make them a recorded whole product */
+	const size_t nitems = dq->items.size();
+	if (!fma && !dq->mul.active && nitems >= 2 && !dq->inverse
+			&& ntt_small_product_supported((unsigned) dq->log2n, mod)
+			&& dq->products.size() < PRODUCTS_MAX) {
+		const defer_item &ia = dq->items[nitems - 2], &ib = dq->items[nitems - 1];
+		struct vkhel_ntt_tables *ntt = dq->tables[ia.table];
+		const void *rp = result->device.ptr;
+		const bool operands = (ia.result == a && ib.result == b)
+			|| (ia.result == b && ib.result == a);
+		if (operands && a != b && dq->tables[ib.table] == ntt && ntt->q == mod
+				&& ntt->n == len && a->length == len && b->length == len
+				&& !dq->reads.count(rp) && !dq->writes.count(rp)
+				&& (dq->products.empty() || dq->product_tables == ntt)) {
+			dq->triple.active = true;
+			dq->triple.fa = ia.result == a ? ia : ib;
+			dq->triple.fb = ia.result == a ? ib : ia;
+			dq->triple.ntt = ntt;
+			dq->items.pop_back();
+			dq->items.pop_back();
+			if (dq->items.empty()) {
+				dq->tables.clear();
+			}
+			dq->writes.insert(rp);
+			dq->mul.active = true;
+			dq->mul.fma = false;
+			dq->mul.with_forwards = true;
+			dq->mul.a = a;
+			dq->mul.b = b;
+			dq->mul.result = result;
+			dq->mul.mod = mod;
+			dq->mul.multiplier = 0;
+			return true;
+		}
+	}
+	defer_flush(result->ctx);   /* what was recorded so far goes first */
 	dq->mul.active = true;
+	dq->mul.with_forwards = false;
 	dq->mul.fma = fma;
 	dq->mul.a = a;
 	dq->mul.b = b;
