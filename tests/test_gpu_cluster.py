@@ -39,7 +39,10 @@ for log2n, limbs, batch in [(14, 1, 1), (14, 3, 5), (15, 1, 7), (15, 2, 3),
     a, b = ctx.from_host(x), ctx.vector(x.size + 3)
     before = ctx.launch_count
     ctx.forward_transform_rns(a, b, tabs, batch)          # out of place
-    assert ctx.launch_count - before == 1 or SLICED, "one launch per transform"
+    # one launch per transform -- two when the RNS batch is cut in two limb
+    # slices for the two streams (8 MiB and more, kernels_ntt.cu)
+    launched = ctx.launch_count - before
+    assert launched == 1 or SLICED or (limbs > 1 and launched == 2), launched
     assert np.array_equal(b.to_host()[:x.size], want), ("forward", log2n, limbs, batch)
     assert np.array_equal(a.to_host(), x), "operand modified"
     ctx.inverse_transform_rns(b, b, tabs, batch)          # in place

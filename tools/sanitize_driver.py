@@ -9,13 +9,42 @@ import sys
 
 import numpy as np
 
+# small RNS batches already take the two-stream limb slices with the lazy join
+os.environ.setdefault("VKHEL_SPLIT_SMALL_MIB", "0.25")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle  # noqa: E402
 import vkhel_b200 as vk  # noqa: E402
 from vkhel_b200 import params  # noqa: E402
 
 
+def variants():
+    """the opt-in kernels: thread-block-cluster single pass ($VKHEL_CLUSTER=1)
+    and the TMA tensor-map column load ($VKHEL_COLS_TMA=1); run with both set"""
+    rng = np.random.default_rng(1)
+    ctx = vk.Context(0)
+    for log2n, limbs, batch in [(14, 2, 2), (15, 1, 3), (16, 2, 1)]:
+        n = 1 << log2n
+        primes = params.ntt_primes(limbs)
+        tabs = [vk.NttTables(n, q, params.find_psi(n, q)) for q in primes]
+        oras = [oracle.Tables(n, q, t.w) for q, t in zip(primes, tabs)]
+        x = np.concatenate([rng.integers(0, primes[p % limbs], n, dtype=np.uint64)
+                            for p in range(limbs * batch)])
+        a, b = ctx.from_host(x), ctx.vector(x.size)
+        ctx.forward_transform_rns(a, b, tabs, batch)
+        assert np.array_equal(b.to_host(), oracle.forward_batch(x, oras, threads=4))
+        ctx.inverse_transform_rns(b, b, tabs, batch)
+        assert np.array_equal(b.to_host(), x)
+        a.destroy(), b.destroy()
+        for t in tabs:
+            t.destroy()
+    ctx.destroy()
+    print("sanitize driver ok")
+
+
 def main():
+    if "--variants" in sys.argv:
+        return variants()
     rng = np.random.default_rng(0)
     ctx = vk.Context(0)
     # (log2n, limbs, batch): row-only, column+row (several tile shapes),
@@ -85,6 +114,50 @@ def main():
         for vec in vs + more:
             vec.destroy()
         t2.destroy()
+    # a loop of the reference's four-call products at small n: recorded whole
+    # products, one launch (inline pointer table for 3, device table for 7)
+    for log2n, count in ((5, 3), (9, 7)):
+        n, q = 1 << log2n, params.P0
+        t3 = vk.NttTables(n, q, params.find_psi(n, q))
+        o3 = oracle.Tables(n, q, t3.w)
+        xs = [rng.integers(0, q, n, dtype=np.uint64) for _ in range(2 * count)]
+        va = [ctx.from_host(x) for x in xs[:count]]
+        vb = [ctx.from_host(x) for x in xs[count:]]
+        vc = [ctx.vector(n) for _ in range(count)]
+        for i in range(count):
+            ctx.forward_transform(va[i], va[i], t3)
+            ctx.forward_transform(vb[i], vb[i], t3)
+            ctx.elemmul(va[i], vb[i], vc[i], q)
+            ctx.inverse_transform(vc[i], vc[i], t3)
+        for i in range(count):                     # maps with read-ahead
+            prod = oracle.elemmul(oracle.forward(xs[i], o3),
+                                  oracle.forward(xs[count + i], o3), q)
+            assert np.array_equal(vc[i].to_host(), oracle.inverse(prod, o3))
+        # the point-wise add folded into the inverse transform
+        ctx.elemfma(va[0], vb[0], vc[0], 1, q)
+        ctx.inverse_transform(vc[0], vc[0], t3)
+        want = oracle.inverse(oracle.elemfma(va[0].to_host(), vb[0].to_host(),
+                                             1, q), o3)
+        assert np.array_equal(vc[0].to_host(), want)
+        for vec in va + vb + vc:
+            vec.destroy()
+        t3.destroy()
+    # limb slices on two streams with the lazy join: a chain of transforms of
+    # the same vector, then an element-wise operation that has to join
+    n, limbs, batch = 1 << 12, 4, 4
+    primes = params.ntt_primes(limbs)
+    tabs = [vk.NttTables(n, q, params.find_psi(n, q)) for q in primes]
+    x = np.concatenate([rng.integers(0, primes[p % limbs], n, dtype=np.uint64)
+                        for p in range(limbs * batch)])
+    a, b = ctx.from_host(x), ctx.vector(x.size)
+    for _ in range(2):
+        ctx.forward_transform_rns(a, b, tabs, batch)
+        ctx.inverse_transform_rns(b, b, tabs, batch)
+    ctx.elemgtadd(b, b, 0, 0)
+    assert np.array_equal(b.to_host(), x)
+    a.destroy(), b.destroy()
+    for t4 in tabs:
+        t4.destroy()
     q = 769
     a = ctx.from_host(rng.integers(0, 1 << 62, 1001, dtype=np.uint64))
     c = ctx.vector(1001)
