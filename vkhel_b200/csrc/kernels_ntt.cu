@@ -1959,7 +1959,9 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		}
 	} else if (!forced && by_limb && units >= 2 && lazy_join()
 			&& split_small_bytes() && total >= split_small_bytes()) {
-		/* fits in L2: two halves, one per stream */
+		/* fits in L2: two limb halves, one per stream.  (A single-modulus
+		 * batch cut in two batch ranges gains nothing: n = 2^14 x 256, 43.4 us
+		 * against 42.1 us forward.) */
 		per = (units + 1) / 2;
 	}
 	const uint64_t nslices = per ? (units + per - 1) / per : 0;
