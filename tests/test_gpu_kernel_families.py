@@ -12,7 +12,8 @@ kernel (kernels_ntt_cluster.cu; more shapes in tests/test_gpu_cluster.py),
 $VKHEL_COLS_TMA=1 loads the forward column tiles of n = 2^16 by TMA tensor map
 (kernels_ntt_tma.cu) and
 $VKHEL_SLICE_MIB=0.0625 cuts every two-pass batch above 192 KiB into slices on two
-streams; they are read once per process, so the parity tests are re-run in
+streams (four with $VKHEL_SLICE_STREAMS=4; joined after every call with
+$VKHEL_LAZY_JOIN=0); they are read once per process, so the parity tests are re-run in
 child processes."""
 import os
 import subprocess
@@ -37,11 +38,15 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
                                     "VKHEL_SINGLE_MAX_LOG2N=13",
                                     "VKHEL_CLUSTER=1",
                                     "VKHEL_COLS_TMA=1",
-                                    "VKHEL_SLICE_MIB=0.0625"])
+                                    "VKHEL_SLICE_MIB=0.0625",
+                                    "VKHEL_SLICE_MIB=0.0625,VKHEL_SLICE_STREAMS=4",
+                                    "VKHEL_SLICE_MIB=0.0625,VKHEL_LAZY_JOIN=0",
+                                    "VKHEL_NO_SMALL_PRODUCT"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)
-    name, _, value = switch.partition("=")
-    env[name] = value or "1"
+    for one in switch.split(","):
+        name, _, value = one.partition("=")
+        env[name] = value or "1"
     res = subprocess.run(
         [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
          "-p", "no:cacheprovider", "-k", SELECT,
