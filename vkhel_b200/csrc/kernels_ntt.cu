@@ -1257,7 +1257,15 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		hgroup_log2++;
 	}
 	/* two rounds of items per CTA amortise the twiddle staging */
-	u64 bchunk = (ROWS_ROUNDS_PER_CTA * slots) >> hgroup_log2;
+	/* ($VKHEL_ROWS_ROUNDS=1: one round per CTA, twice the CTAs.  Measured: n =
+	 * 2^14 x 256 forward 40.8 against 42.3 us, the 8-GPU shard of the bench
+	 * 79.0 against 79.3 us, the full bench 631.3 against 627.8 us -- a rule
+	 * that picks by grid size gained nothing overall, two stays the default) */
+	static const int rounds_env = getenv("VKHEL_ROWS_ROUNDS")
+		? atoi(getenv("VKHEL_ROWS_ROUNDS")) : 0;
+	const u64 rounds = rounds_env == 1 || rounds_env == 2 ? (u64) rounds_env
+		: ROWS_ROUNDS_PER_CTA;
+	u64 bchunk = (rounds * slots) >> hgroup_log2;
 	if (bchunk < (u64) NP) {
 		bchunk = NP;
 	}
