@@ -429,6 +429,39 @@ def product_quad(ctx, a, b, c, t, swap=False):
     ctx.inverse_transform(c, c, t.lib)
 
 
+@pytest.mark.parametrize("log2n,count", [(12, 1), (12, 9), (13, 20), (14, 5),
+                                         (16, 3), (17, 2)])
+def test_loop_of_products_at_two_pass_sizes_is_four_launches(ctx, log2n, count):
+    """The same loop above n = 2^11: the forward transforms of all products
+    stay in the record and go out as one indirect batch, the inverse
+    transforms of the products as a second one that multiplies while it loads
+    -- four launches for the whole loop instead of four per product."""
+    n, q = 1 << log2n, params.P0
+    t = Tables(n, q)
+    rng = np.random.default_rng(7200 + log2n)
+    xs = [rand_mod(rng, n, q) for _ in range(count)]
+    ys = [rand_mod(rng, n, q) for _ in range(count)]
+    va = [ctx.from_host(x) for x in xs]
+    vb = [ctx.from_host(y) for y in ys]
+    vc = [ctx.vector(n) for _ in range(count)]
+    ctx.sync()
+    l0, f0 = ctx.launch_count, ctx.fused_products
+    for i in range(count):
+        product_quad(ctx, va[i], vb[i], vc[i], t, swap=bool(i & 1))
+    assert ctx.launch_count_noflush == l0
+    ctx.flush()
+    assert ctx.launch_count == l0 + 4
+    assert ctx.fused_products == f0 + count
+    for i in range(count):
+        fx, fy = oracle.forward(xs[i], t.ora), oracle.forward(ys[i], t.ora)
+        assert np.array_equal(vc[i].to_host(), product_oracle(fx, fy, t)), i
+        assert np.array_equal(va[i].to_host(), fx), i
+        assert np.array_equal(vb[i].to_host(), fy), i
+    for v in va + vb + vc:
+        v.destroy()
+    t.destroy()
+
+
 @pytest.mark.parametrize("log2n,count", [(3, 5), (4, 3), (6, 9), (8, 40),
                                          (9, 7), (10, 33), (11, 6)])
 def test_loop_of_small_products_is_one_launch(ctx, log2n, count):
@@ -462,8 +495,11 @@ def test_loop_of_small_products_is_one_launch(ctx, log2n, count):
     t.destroy()
 
 
-def test_small_products_out_of_place_reused_vectors_and_interruptions(ctx):
-    n, q = 1 << 10, params.P0
+@pytest.mark.parametrize("log2n", [10, 13])
+def test_recorded_products_out_of_place_reused_vectors_and_interruptions(ctx, log2n):
+    """whole products (n = 2^10) and batched inverse-of-products (n = 2^13)
+    under every way of not completing the four-call sequence"""
+    n, q = 1 << log2n, params.P0
     t = Tables(n, q)
     t2 = Tables(n, params.Q61)
     rng = np.random.default_rng(7100)

@@ -40,8 +40,7 @@ SELECT = ("ntt_random_all_sizes or ntt_random_large or kat or batch_matches "
                                     "VKHEL_COLS_TMA=1",
                                     "VKHEL_SLICE_MIB=0.0625",
                                     "VKHEL_SLICE_MIB=0.0625,VKHEL_SLICE_STREAMS=4",
-                                    "VKHEL_SLICE_MIB=0.0625,VKHEL_LAZY_JOIN=0",
-                                    "VKHEL_NO_SMALL_PRODUCT"])
+                                    "VKHEL_SLICE_MIB=0.0625,VKHEL_LAZY_JOIN=0"])
 def test_parity_with_forced_family(switch):
     env = dict(os.environ)
     for one in switch.split(","):

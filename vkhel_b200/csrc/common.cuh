@@ -67,6 +67,7 @@ struct limb_desc {
 struct ntt_ptrs {
 	const u64 *src;
 	u64 *dst;
+	const u64 *src2;   /* second factor of a recorded inverse-of-product, else unused */
 };
 
 /* device.cu */
@@ -137,7 +138,11 @@ bool ntt_indirect_supported(unsigned log2n, uint64_t q);
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
 		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max,
-		const ntt_ptrs *host_tab = NULL);
+		const ntt_ptrs *host_tab = NULL, bool product = false);
+/* `product` (inverse only): polynomial i is the inverse transform of the
+ * point-wise product tab[i].src * tab[i].src2 (the reference's elemmul followed
+ * by the in-place inverse transform), where ntt_indirect_product_supported() */
+bool ntt_indirect_product_supported(unsigned log2n, uint64_t q);
 
 /* kernels_ntt_cluster.cu: single-pass transform of 2^14 <= n <= 2^16 on a
  * thread-block cluster (polynomial distributed over the CTAs' shared memory);

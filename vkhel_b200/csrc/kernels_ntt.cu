@@ -330,6 +330,7 @@ struct fast_pass {
 	const u64 *src;
 	const u64 *src2;      /* row pass, MUL: second operand of the fused point-wise op */
 	u64 fma_mult;         /* MUL: 0 = product src*src2, else src*fma_mult + src2 */
+	bool mul;             /* the row pass of this transform multiplies while it loads */
 	u64 *dst;
 	const limb_desc *descs;
 	unsigned limbs;
@@ -461,7 +462,6 @@ __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 	static_assert(INV || !TOP, "TOP distinguishes inverse passes only");
-	static_assert(!(IND && MUL), "no indirect fused product");
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -549,13 +549,15 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 			active[pp] = idx < nitems && bl < nb;
 			const u64 poly = (b0 + bl) * p.limbs_total + p.limb0 + limb;
 			const u64 *sp;
+			const u64 *src2base = p.src2;   /* MUL only */
 			if (IND) {
 				off[pp] = (u64) (H0 + h) << K;
-				ntt_ptrs ent = { NULL, NULL };
+				ntt_ptrs ent = { NULL, NULL, NULL };
 				if (active[pp]) {
 					ent = p.entry(poly);
 				}
 				dbase[pp] = ent.dst;
+				src2base = ent.src2;
 				sp = (p.tab_second ? ent.dst : ent.src) + off[pp] + tb_first;
 			} else {
 				off[pp] = (poly << L) + ((u64) (H0 + h) << K);
@@ -588,7 +590,7 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 				m.v = d.mm_v;
 				m.s = d.mm_s;
 				m.mu = 0;
-				const u64 *sp2 = p.src2 + off[pp] + tb_first;
+				const u64 *sp2 = src2base + off[pp] + tb_first;
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
 					const u64 y = active[pp] ? sp2[G::eoff(first, e)] : 0;
@@ -1282,18 +1284,16 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 	/* inverse: the variant that holds stage 0 (and n^-1), or the plain one */
 	const bool top = INV && p.s0 == 0;
 	void (*kernel)(fast_pass);
-	if constexpr (!MUL) {
-		if (p.indirect()) {
-			if constexpr (INV) {
-				kernel = top ? ntt_rows_kernel<INV, K, NP, false, APX, true, true>
-					: ntt_rows_kernel<INV, K, NP, false, APX, true, false>;
-			} else {
-				kernel = ntt_rows_kernel<INV, K, NP, false, APX, true, false>;
-			}
-			launch_fast_optin(ctx, kernel, (unsigned) blocks, FAST_THREADS,
-					smem, p);
-			return;
+	if (p.indirect()) {
+		if constexpr (INV) {
+			kernel = top ? ntt_rows_kernel<INV, K, NP, MUL, APX, true, true>
+				: ntt_rows_kernel<INV, K, NP, MUL, APX, true, false>;
+		} else {
+			kernel = ntt_rows_kernel<INV, K, NP, false, APX, true, false>;
 		}
+		launch_fast_optin(ctx, kernel, (unsigned) blocks, FAST_THREADS,
+				smem, p);
+		return;
 	}
 	if constexpr (INV) {
 		kernel = top ? ntt_rows_kernel<INV, K, NP, MUL, APX, false, true>
@@ -1307,7 +1307,7 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 template <bool INV, int K, bool APX>
 static void run_rows(struct vkhel_ctx *ctx, const fast_pass &p) {
 	if constexpr (INV) {
-		if (p.src2) {
+		if (p.mul) {
 			run_rows_np<INV, K, 1, true, APX>(ctx, p);
 			return;
 		}
@@ -1448,7 +1448,8 @@ static void run_single(struct vkhel_ctx *ctx, fast_pass p) {
 	const size_t smem = (sizeof(ulonglong2) << K)
 		+ sizeof(u64) * (size_t) (xpad(1 << K) + 4);
 	if constexpr (INV) {
-		if (p.src2) {
+		if (p.mul) {
+			VK_REQUIRE(!p.indirect(), "internal: indirect product in one pass");
 			if (smem_needs_optin(smem)) {
 				CUDA_CHECK(cudaFuncSetAttribute(
 							ntt_single_kernel<true, K, APX, false, true>,
@@ -1587,11 +1588,13 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
 		unsigned log2n, const u64 *src2 = NULL, const ntt_ptrs *tab = NULL,
 		unsigned limbs_total = 0, unsigned limb0 = 0,
-		const ntt_ptrs *inline_tab = NULL, u64 fma_mult = 0) {
+		const ntt_ptrs *inline_tab = NULL, u64 fma_mult = 0,
+		bool ind_product = false) {
 	const fast_plan pl = plan_fast(log2n, !INV);
 	fast_pass p;
 	p.zero = 0;
 	p.fma_mult = fma_mult;
+	p.mul = false;
 	p.tab = tab;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -1617,6 +1620,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	if ((!src2 || INV) && log2n >= 9 && log2n <= single_max_log2n()) {
 		p.src = src;
 		p.src2 = INV ? src2 : NULL;
+		p.mul = INV && src2 != NULL;
 		p.dst = dst;
 		p.s0 = 0;
 		run_single_k<INV, APX>(ctx, p, log2n);
@@ -1663,12 +1667,14 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	} else {
 		p.src = src;
 		p.src2 = src2;
+		p.mul = src2 != NULL || ind_product;
 		p.dst = dst;
 		p.s0 = pl.lead + pl.kcol;
 		if (!pl.kcol || only_pass() != 1) {
 			run_rows_k<true, APX>(ctx, p, pl.krow);
 		}
 		p.src2 = NULL;
+		p.mul = false;
 		p.tab_second = 1;
 		if (pl.kcol && only_pass() != 2) {
 			p.src = dst;
@@ -1742,6 +1748,7 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	fast_pass p;
 	p.zero = 0;
 	p.fma_mult = 0;
+	p.mul = false;
 	p.tab = NULL;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -2107,19 +2114,29 @@ bool ntt_indirect_supported(unsigned log2n, uint64_t q) {
 	return !force_generic && q < (1ull << 62) && log2n >= 3 && log2n <= 18;
 }
 
+bool ntt_indirect_product_supported(unsigned log2n, uint64_t q) {
+	/* two-pass sizes: below them the whole product is one CTA
+	 * (kernels_ntt_small.cu), and the single-pass kernel has no indirect
+	 * product */
+	return ntt_indirect_supported(log2n, q) && log2n > single_max_log2n()
+		&& log2n > 8;
+}
+
 void launch_ntt_indirect(struct vkhel_ctx *ctx, bool inverse,
 		const ntt_ptrs *tab, const limb_desc *descs, uint64_t limbs,
 		uint64_t polys, unsigned log2n, uint64_t q_max,
-		const ntt_ptrs *host_tab) {
+		const ntt_ptrs *host_tab, bool product) {
 	VK_REQUIRE(ntt_indirect_supported(log2n, q_max),
 			"internal: indirect batch outside the fast path");
 	VK_REQUIRE((tab != NULL) != (host_tab != NULL),
 			"internal: indirect batch needs exactly one pointer table");
+	VK_REQUIRE(!product || (inverse && ntt_indirect_product_supported(log2n, q_max)),
+			"internal: indirect product outside its range");
 	if (use_approx(q_max, log2n)) {
-		if (inverse) run_fast<true, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
+		if (inverse) run_fast<true, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab, 0, product);
 		else run_fast<false, true>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
 	} else {
-		if (inverse) run_fast<true, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
+		if (inverse) run_fast<true, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab, 0, product);
 		else run_fast<false, false>(ctx, NULL, NULL, descs, limbs, polys, log2n, NULL, tab, 0, 0, host_tab);
 	}
 }

@@ -66,6 +66,11 @@ struct pending_product {
 	/* the two forward transforms that produced a and b are held back with it
 	 * (defer_queue::triple): a candidate for a recorded whole product */
 	bool with_forwards;
+	/* the two forward transforms that produce a and b are still in the record
+	 * (two-pass sizes): they have to be launched before this product, and the
+	 * matching inverse transform makes it a recorded inverse-of-product */
+	bool after_items;
+	struct vkhel_ntt_tables *ntt;   /* after_items: the forward transforms' tables */
 	const struct vkhel_vector *a, *b;
 	struct vkhel_vector *result;
 	uint64_t mod, multiplier;
@@ -85,6 +90,12 @@ struct defer_queue {
 	std::vector<small_product> products;   /* complete four-call products */
 	std::vector<struct vkhel_vector *> product_results;
 	struct vkhel_ntt_tables *product_tables;
+	/* recorded inverse transforms of a product (two-pass sizes): launched as
+	 * one indirect batch after the recorded transforms, which produce their
+	 * factors */
+	std::vector<ntt_ptrs> inv_products;
+	std::vector<struct vkhel_vector *> inv_product_results;
+	struct vkhel_ntt_tables *inv_product_tables;
 	bool inverse;
 	uint64_t log2n;
 	std::vector<struct vkhel_ntt_tables *> tables;   /* distinct, <= DEFER_TABLES */
@@ -105,8 +116,10 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 		defer_queue *dq = new defer_queue();
 		dq->mul.active = false;
 		dq->mul.with_forwards = false;
+		dq->mul.after_items = false;
 		dq->triple.active = false;
 		dq->product_tables = NULL;
+		dq->inv_product_tables = NULL;
 		dq->inverse = false;
 		dq->log2n = 0;
 		dq->half = 0;
@@ -125,12 +138,13 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
  * [batch][limbs] (polynomial i uses descs[i % limbs]) */
 static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 		const std::vector<ntt_ptrs> &host, const limb_desc *descs,
-		uint64_t limbs, uint64_t q_max) {
+		uint64_t limbs, uint64_t q_max, bool inverse, unsigned log2n,
+		bool product = false) {
 	const size_t count = host.size();
 	if (count <= NTT_INLINE_PTRS) {
 		/* short record: the pointers travel in the kernel parameters */
-		launch_ntt_indirect(ctx, dq->inverse, NULL, descs, limbs, count,
-				(unsigned) dq->log2n, q_max, host.data());
+		launch_ntt_indirect(ctx, inverse, NULL, descs, limbs, count,
+				log2n, q_max, host.data(), product);
 		ctx->dev.deferred_batches++;
 		ctx->dev.deferred_transforms += count;
 		return;
@@ -151,8 +165,8 @@ static void defer_launch(struct vkhel_ctx *ctx, defer_queue *dq,
 		CUDA_CHECK(cudaMemcpyAsync(tab, dq->stage[h], piece * sizeof(ntt_ptrs),
 					cudaMemcpyHostToDevice, ctx_stream(ctx)));
 		CUDA_CHECK(cudaEventRecord(dq->staged[h], ctx_stream(ctx)));
-		launch_ntt_indirect(ctx, dq->inverse, tab, descs, limbs, piece,
-				(unsigned) dq->log2n, q_max);
+		launch_ntt_indirect(ctx, inverse, tab, descs, limbs, piece,
+				log2n, q_max, NULL, product);
 		device_free(ctx, tab);   /* stream-ordered: after the kernels */
 		ctx->dev.deferred_batches++;
 		ctx->dev.deferred_transforms += piece;
@@ -307,59 +321,19 @@ static void readahead_advance(struct vkhel_vector *vec) {
 	}
 }
 
-void defer_flush(struct vkhel_ctx *ctx) {
-	/* everything that is about to use the context's stream comes through
-	 * here: slices still on the auxiliary stream are joined first */
-	defer_queue *dq = (defer_queue *) ctx->dev.defer;
-	/* (a batched transform that may continue the slices holds the join back
-	 * while it fetches its pointers -- but not if recorded work is launched
-	 * here, which goes to the context's stream and may touch the same vector) */
-	if (!ctx->dev.split_hold
-			|| (dq && (!dq->items.empty() || !dq->products.empty()
-					|| dq->mul.active))) {
-		ntt_split_join(ctx);
-	}
-	if (!dq) {
-		return;
-	}
-	if (dq->items.empty() && dq->products.empty()) {
-		flush_product(ctx, dq);   /* (with its forward transforms, if held) */
-		dq->tables.clear();
-		dq->reads.clear();
-		dq->writes.clear();
-		return;
-	}
-	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+/* launch the recorded transforms (regrouped by tables) and forget them */
+static void launch_recorded_items(struct vkhel_ctx *ctx, defer_queue *dq) {
 	const size_t count = dq->items.size();
 	const size_t ntab = dq->tables.size();
-	/* the vectors a loop of maps is likely to ask for next (read-ahead) */
-	readahead_list *ra = readahead_get(ctx);
-	ra->results.clear();
-	if (count + dq->product_results.size() > 1) {
-		for (const defer_item &it : dq->items) {
-			ra->results.push_back(it.result);
-		}
-		for (struct vkhel_vector *v : dq->product_results) {
-			ra->results.push_back(v);
-		}
-	}
-	/* recorded transforms, recorded products and a held product are
-	 * independent of each other (the read/write sets): any order will do */
-	launch_recorded_products(ctx, dq);
-	flush_product(ctx, dq);
 	if (!count) {
 		dq->tables.clear();
-		dq->reads.clear();
-		dq->writes.clear();
 		return;
 	}
+	const unsigned log2n = (unsigned) dq->log2n;
 	/* An indirect batch costs a pointer-table copy on top of its launches;
 	 * a record that short is cheaper launched transform by transform:
-	 * always a single one, and two where a transform is one launch (the
-	 * two forward transforms of the reference's product at n <= 2^11:
-	 * measured 12.3 us per product this way against 16.1 us batched). */
-	if (count == 1 || (count == 2
-				&& ntt_launches_per_transform((unsigned) dq->log2n) == 1)) {
+	 * always a single one, and two where a transform is one launch. */
+	if (count == 1 || (count == 2 && ntt_launches_per_transform(log2n) == 1)) {
 		for (const defer_item &it : dq->items) {
 			struct vkhel_ntt_tables *ntt = dq->tables[it.table];
 			launch_ntt(ctx, dq->inverse, it.ptrs.src, it.ptrs.dst,
@@ -396,7 +370,7 @@ void defer_flush(struct vkhel_ctx *ctx) {
 			}
 			defer_launch(ctx, dq, host,
 					rns_plan_device_descs(ctx, dq->tables.data(), ntab), ntab,
-					q_max);
+					q_max, dq->inverse, log2n);
 		} else {
 			for (size_t t = 0; t < ntab; t++) {
 				struct vkhel_ntt_tables *ntt = dq->tables[t];
@@ -410,13 +384,70 @@ void defer_flush(struct vkhel_ctx *ctx) {
 							(unsigned) ntt->log2n, ntt->q);
 				} else {
 					defer_launch(ctx, dq, by_table[t],
-							ntt_tables_device_desc(ctx, ntt), 1, ntt->q);
+							ntt_tables_device_desc(ctx, ntt), 1, ntt->q,
+							dq->inverse, log2n);
 				}
 			}
 		}
 	}
 	dq->items.clear();
 	dq->tables.clear();
+}
+
+/* the recorded inverse transforms of products, one indirect batch */
+static void launch_recorded_inverse_products(struct vkhel_ctx *ctx,
+		defer_queue *dq) {
+	if (dq->inv_products.empty()) {
+		return;
+	}
+	struct vkhel_ntt_tables *ntt = dq->inv_product_tables;
+	defer_launch(ctx, dq, dq->inv_products, ntt_tables_device_desc(ctx, ntt), 1,
+			ntt->q, true, (unsigned) ntt->log2n, true);
+	dq->inv_products.clear();
+	dq->inv_product_results.clear();
+	dq->inv_product_tables = NULL;
+}
+
+void defer_flush(struct vkhel_ctx *ctx) {
+	/* everything that is about to use the context's stream comes through
+	 * here: slices still on the auxiliary stream are joined first */
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	const bool recorded = dq && (!dq->items.empty() || !dq->products.empty()
+			|| !dq->inv_products.empty());
+	/* (a batched transform that may continue the slices holds the join back
+	 * while it fetches its pointers -- but not if recorded work is launched
+	 * here, which goes to the context's stream and may touch the same vector) */
+	if (!ctx->dev.split_hold || recorded || (dq && dq->mul.active)) {
+		ntt_split_join(ctx);
+	}
+	if (!dq) {
+		return;
+	}
+	if (recorded) {
+		CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+		/* the vectors a loop of maps is likely to ask for next (read-ahead) */
+		readahead_list *ra = readahead_get(ctx);
+		ra->results.clear();
+		if (dq->items.size() + dq->product_results.size()
+				+ dq->inv_product_results.size() > 1) {
+			for (const defer_item &it : dq->items) {
+				ra->results.push_back(it.result);
+			}
+			for (struct vkhel_vector *v : dq->product_results) {
+				ra->results.push_back(v);
+			}
+			for (struct vkhel_vector *v : dq->inv_product_results) {
+				ra->results.push_back(v);
+			}
+		}
+	}
+	/* Order: recorded whole products are independent of everything else; the
+	 * recorded transforms come before a held product and before the recorded
+	 * inverse-of-products, whose factors they produce. */
+	launch_recorded_products(ctx, dq);
+	launch_recorded_items(ctx, dq);
+	flush_product(ctx, dq);   /* (with its forward transforms, if it holds them) */
+	launch_recorded_inverse_products(ctx, dq);
 	dq->reads.clear();
 	dq->writes.clear();
 }
@@ -427,7 +458,9 @@ void defer_flush_tables(struct vkhel_ctx *ctx,
 	if (!dq) {
 		return;
 	}
-	if (dq->product_tables == ntt || (dq->triple.active && dq->triple.ntt == ntt)) {
+	if (dq->product_tables == ntt || dq->inv_product_tables == ntt
+			|| (dq->triple.active && dq->triple.ntt == ntt)
+			|| (dq->mul.active && dq->mul.after_items && dq->mul.ntt == ntt)) {
 		defer_flush(ctx);
 		return;
 	}
@@ -473,7 +506,8 @@ static bool defer_transform(bool inverse, const struct vkhel_vector *operand,
 	flush_product(ctx, dq);
 	const void *rd = operand->device.ptr, *wr = result->device.ptr;
 	unsigned table = 0;
-	if (!dq->items.empty() || !dq->products.empty()) {
+	if (!dq->items.empty() || !dq->products.empty()
+			|| !dq->inv_products.empty()) {
 		while (table < dq->tables.size() && dq->tables[table] != ntt) {
 			table++;
 		}
@@ -527,12 +561,19 @@ static inline u64 *dev_u64(const struct vkhel_vector *v) {
  *     been held back.
  * $VKHEL_NO_DEFER=1 turns this off together with the recorded transforms,
  * $VKHEL_NO_FUSED_PRODUCT=1 only this. */
+static void launch_recorded_items(struct vkhel_ctx *ctx, defer_queue *dq);
+
 static void flush_product(struct vkhel_ctx *ctx, defer_queue *dq) {
 	if (!dq->mul.active) {
 		return;
 	}
 	dq->mul.active = false;
 	CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+	if (dq->mul.after_items) {
+		/* its factors are results of recorded transforms */
+		dq->mul.after_items = false;
+		launch_recorded_items(ctx, dq);
+	}
 	if (dq->mul.with_forwards) {
 		/* the product did not become a recorded whole product: its two
 		 * forward transforms, taken out of the record, go first */
@@ -590,6 +631,27 @@ static bool fuse_product_into_inverse(const struct vkhel_vector *operand,
 			return true;
 		}
 		return false;   /* the caller's path launches the three held calls */
+	}
+	if (m.after_items) {
+		if (operand == result && result == m.result && ntt == m.ntt) {
+			/* forward, forward, elemmul, inverse at a two-pass size: the
+			 * inverse transform of the product is recorded; it goes out with
+			 * those of the other products of the loop, after the recorded
+			 * forward transforms */
+			ntt_ptrs ent;
+			ent.src = dev_u64_nodefer(m.a);
+			ent.src2 = dev_u64_nodefer(m.b);
+			ent.dst = dev_u64_nodefer(result);
+			dq->inv_products.push_back(ent);
+			dq->inv_product_results.push_back(result);
+			dq->inv_product_tables = ntt;
+			dq->mul.active = false;
+			dq->mul.after_items = false;
+			ctx->dev.fused_products++;
+			ctx->dev.deferred_transforms++;
+			return true;
+		}
+		return false;   /* the caller's path launches transforms and product */
 	}
 	if (operand != result || result != m.result || m.mod != ntt->q
 			|| result->length != ntt->n || !dq->items.empty()) {
@@ -963,15 +1025,39 @@ static bool record_pointwise(bool fma, const struct vkhel_vector *a,
 	 * recorded calls: hold all three for the inverse transform that would
 	 * make them a recorded whole product */
 	const size_t nitems = dq->items.size();
+	const bool small = ntt_small_product_supported((unsigned) dq->log2n, mod);
+	static const bool no_batch = getenv("VKHEL_NO_BATCHED_PRODUCT") != NULL;
 	if (!fma && !dq->mul.active && nitems >= 2 && !dq->inverse
-			&& ntt_small_product_supported((unsigned) dq->log2n, mod)
-			&& dq->products.size() < PRODUCTS_MAX) {
+			&& (small ? dq->products.size() < PRODUCTS_MAX
+				: !no_batch && ntt_indirect_product_supported(
+					(unsigned) dq->log2n, mod)
+				&& dq->inv_products.size() < DEFER_MAX)) {
 		const defer_item &ia = dq->items[nitems - 2], &ib = dq->items[nitems - 1];
 		struct vkhel_ntt_tables *ntt = dq->tables[ia.table];
 		const void *rp = result->device.ptr;
 		const bool operands = (ia.result == a && ib.result == b)
 			|| (ia.result == b && ib.result == a);
 		if (operands && a != b && dq->tables[ib.table] == ntt && ntt->q == mod
+				&& ntt->n == len && a->length == len && b->length == len
+				&& !dq->reads.count(rp) && !dq->writes.count(rp)
+				&& !small) {
+			/* two-pass sizes: the forward transforms stay in the record (a
+			 * loop of products batches them), the product waits behind them */
+			if (dq->inv_products.empty() || dq->inv_product_tables == ntt) {
+				dq->writes.insert(rp);
+				dq->mul.active = true;
+				dq->mul.fma = false;
+				dq->mul.with_forwards = false;
+				dq->mul.after_items = true;
+				dq->mul.ntt = ntt;
+				dq->mul.a = a;
+				dq->mul.b = b;
+				dq->mul.result = result;
+				dq->mul.mod = mod;
+				dq->mul.multiplier = 0;
+				return true;
+			}
+		} else if (operands && a != b && dq->tables[ib.table] == ntt && ntt->q == mod
 				&& ntt->n == len && a->length == len && b->length == len
 				&& !dq->reads.count(rp) && !dq->writes.count(rp)
 				&& (dq->products.empty() || dq->product_tables == ntt)) {
@@ -999,6 +1085,7 @@ static bool record_pointwise(bool fma, const struct vkhel_vector *a,
 	defer_flush(result->ctx);   /* what was recorded so far goes first */
 	dq->mul.active = true;
 	dq->mul.with_forwards = false;
+	dq->mul.after_items = false;
 	dq->mul.fma = fma;
 	dq->mul.a = a;
 	dq->mul.b = b;
