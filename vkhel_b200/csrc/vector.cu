@@ -813,15 +813,6 @@ extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 	char *dst = (char *) dev_u64(vec);
 	const char *src = (const char *) elements;
 	size_t left = vec->device.bytes;
-	if (left <= ((size_t) 64 << 10)) {
-		/* small vectors: the driver stages a pageable source of this size
-		 * itself faster than a trip through the staging cache (the call
-		 * returns once the source has been read; measured from C, 1024
-		 * polynomials of 32 KiB: 6.2 against 7.9 ms) */
-		CUDA_CHECK(cudaMemcpyAsync(dst, src, left, cudaMemcpyHostToDevice,
-					ctx_stream(ctx)));
-		return;
-	}
 	while (left) {
 		const size_t piece = left < STAGE_CHUNK_BYTES ? left : STAGE_CHUNK_BYTES;
 		void *stage = pinned_acquire(ctx, piece);
