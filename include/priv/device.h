@@ -52,6 +52,7 @@ struct device_ctx {
 	 * entry points while they fetch their pointers, so that this one flush does
 	 * not join. */
 	int split_active, split_hold, split_by_limb;
+	int in_slices;       /* kernels being launched belong to a sliced transform */
 	const void *split_dst;
 	size_t split_bytes;
 	uint64_t split_per, split_units;

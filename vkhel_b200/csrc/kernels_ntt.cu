@@ -1259,14 +1259,27 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 		hgroup_log2++;
 	}
 	/* two rounds of items per CTA amortise the twiddle staging */
-	/* ($VKHEL_ROWS_ROUNDS=1: one round per CTA, twice the CTAs.  Measured: n =
-	 * 2^14 x 256 forward 40.8 against 42.3 us, the 8-GPU shard of the bench
-	 * 79.0 against 79.3 us, the full bench 631.3 against 627.8 us -- a rule
-	 * that picks by grid size gained nothing overall, two stays the default) */
+	/* One round per CTA -- twice the CTAs, half the ragged last wave -- for a
+	 * launch of fewer than four waves that has the device to itself; slices
+	 * on two streams fill each other's tails and keep two rounds.  Measured: n
+	 * = 2^14 x 256 forward 40.8 against 42.3 us; with one round everywhere the
+	 * full bench loses 0.5 % (631.3 against 627.8 us).  $VKHEL_ROWS_ROUNDS=1|2
+	 * forces either. */
 	static const int rounds_env = getenv("VKHEL_ROWS_ROUNDS")
 		? atoi(getenv("VKHEL_ROWS_ROUNDS")) : 0;
-	const u64 rounds = rounds_env == 1 || rounds_env == 2 ? (u64) rounds_env
-		: ROWS_ROUNDS_PER_CTA;
+	u64 rounds = ROWS_ROUNDS_PER_CTA;
+	if (!ctx->dev.in_slices) {
+		u64 bc2 = (rounds * slots) >> hgroup_log2;
+		bc2 = bc2 < (u64) NP ? NP : bc2 > batch ? batch : bc2;
+		const u64 ctas2 = ((batch + bc2 - 1) / bc2) * p.limbs
+			* ((1ull << p.s0) >> hgroup_log2);
+		if (ctas2 < 4ull * 6 * (u64) ctx->dev.sm_count) {
+			rounds = 1;
+		}
+	}
+	if (rounds_env == 1 || rounds_env == 2) {
+		rounds = (u64) rounds_env;
+	}
 	u64 bchunk = (rounds * slots) >> hgroup_log2;
 	if (bchunk < (u64) NP) {
 		bchunk = NP;
@@ -2004,6 +2017,7 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 	 * stream -- it reads and writes only what that one wrote (or reads a
 	 * vector no pending slice writes) */
 	dev->split_active = 0;
+	dev->in_slices = 1;
 	for (uint64_t i = 0; i < nslices; i++) {
 		const uint64_t u0 = i * per;
 		const uint64_t cnt = units - u0 < per ? units - u0 : per;
@@ -2023,6 +2037,7 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 		}
 	}
 	ctx->dev.launch_stream = NULL;
+	dev->in_slices = 0;
 	if (lazy_join()) {
 		/* the join is left to whoever needs the context's stream next
 		 * (defer_flush -> ntt_split_join), or to nobody if the next call is
