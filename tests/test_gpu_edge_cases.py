@@ -245,6 +245,30 @@ def test_exposed_stream_stops_recording():
     own.elemmul(vs[0], vs[1], vs[2], q)
     assert own.launch_count_noflush > l0
     assert own.deferred_stats == (1, 6) and own.fused_products == 0
+    # ... and a sliced transform joins its two streams before it returns: a
+    # caller's work enqueued on the exposed stream right behind it (here a
+    # plain cudaMemcpyAsync through cuda-python) sees the complete result
+    from cuda.bindings import runtime as rt
+    n2, limbs, batch = 1 << 14, 4, 16
+    primes = params.ntt_primes(limbs)
+    tps = [TablePair(n2, p) for p in primes]
+    x = np.concatenate([rand_mod(rng, n2, primes[i % limbs])
+                        for i in range(limbs * batch)])
+    big = own.from_host(x)
+    ptr = big.device_ptr
+    host = np.empty_like(x)
+    own.forward_transform_rns(big, big, [t.lib for t in tps], batch)
+    err, = rt.cudaMemcpyAsync(host.ctypes.data, ptr, x.nbytes,
+                              rt.cudaMemcpyKind.cudaMemcpyDeviceToHost,
+                              own.stream)
+    assert int(err) == 0
+    err, = rt.cudaStreamSynchronize(own.stream)
+    assert int(err) == 0
+    assert np.array_equal(host, oracle.forward_batch(
+        x, [t.ora for t in tps], threads=8))
+    big.destroy()
+    for t in tps:
+        t.destroy()
     assert np.array_equal(vs[2].to_host(), oracle.elemmul(xs[0], xs[1], q))
     assert np.array_equal(vs[3].to_host(), xs[3])
     for v in vs:

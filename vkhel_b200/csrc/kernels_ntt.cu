@@ -2038,8 +2038,10 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 	}
 	ctx->dev.launch_stream = NULL;
 	dev->in_slices = 0;
-	if (lazy_join()) {
-		/* the join is left to whoever needs the context's stream next
+	if (lazy_join() && !ctx->dev.stream_exposed) {
+		/* (a caller that holds the stream orders its own work by stream
+		 * position: for it every call joins before it returns.)
+		 * The join is left to whoever needs the context's stream next
 		 * (defer_flush -> ntt_split_join), or to nobody if the next call is
 		 * the same partition of the same vector again */
 		dev->split_active = 1;
