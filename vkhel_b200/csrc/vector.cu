@@ -233,6 +233,10 @@ static void launch_recorded_products(struct vkhel_ctx *ctx, defer_queue *dq) {
  * no operation has touched its vector since it was started (ra_op), and costs
  * at most READAHEAD_WINDOW vector copies when the caller stops mapping. */
 #define READAHEAD_WINDOW 3
+/* only vectors up to this size are copied ahead: beyond it a copy takes long
+ * enough to hide the latency of starting it, and a speculative staging buffer
+ * would be large */
+#define READAHEAD_MAX_BYTES ((size_t) 4 << 20)
 
 struct readahead_list {
 	std::vector<struct vkhel_vector *> results;
@@ -311,6 +315,7 @@ static void readahead_advance(struct vkhel_vector *vec) {
 			&& i <= at + READAHEAD_WINDOW; i++) {
 		struct vkhel_vector *next = ra->results[i];
 		if (next && !next->host.ptr && next->length
+				&& next->device.bytes <= READAHEAD_MAX_BYTES
 				&& !(next->ra_ptr && next->ra_op == next->last_op)) {
 			todo[count++] = next;
 		}
