@@ -2,7 +2,7 @@
 """Static SASS census of the hot kernels (no GPU needed): opcode counts per
 kernel from `cuobjdump -sass build/obj/kernels_ntt.o`, grouped the way the
 integer roofline counts them -- IMAD.WIDE / IMAD.HI / IMAD on the fmaheavy
-pipe (2.2 / 3.0 / 1.1 issue slots each, tools/pipe_bench.cu), IADD3 / SEL /
+pipe (2.18 / 2.35 / 1 IMAD slots each as measured by probe.cu), IADD3 / SEL /
 LOP3 on the ALU pipe -- plus the memory and TMA (UBLKCP) instructions.  The
 counts are for the whole kernel text -- prologue, tails, and for the inverse
 kernels TWO copies of the rounds (the pass with and the pass without the n^-1
@@ -28,7 +28,10 @@ KERNELS = [
 ]
 FMA = ("IMAD.WIDE", "IMAD.HI", "IMAD", "IMAD.X", "IMAD.MOV", "IMAD.IADD",
        "IMAD.SHL")
-SLOTS = {"IMAD.WIDE": 2.2, "IMAD.HI": 3.0}
+# IMAD slots per instruction, from vkhel_ctx_probe_int_peaks on the B200
+# (profiles/r02_probe_int_peaks.json): IMAD 63.2, IMAD.WIDE 29.0, IMAD.HI 26.9
+# thread-instructions per clock per SM
+SLOTS = {"IMAD.WIDE": 2.18, "IMAD.HI": 2.35}
 
 
 def group(op):
@@ -59,12 +62,13 @@ def main():
                              body):
             ops[group(m.group(1))] += 1
         total = sum(ops.values())
-        slots = sum(ops[k] * SLOTS.get(k, 1.1) for k in FMA)
+        slots = sum(ops[k] * SLOTS.get(k, 1.0) for k in FMA)
         print("== %s: %d instructions in the kernel text, %d butterflies per "
               "thread per tile" % (label, total, bfly))
         print("   fmaheavy pipe: " + ", ".join("%s %d" % (k, ops[k]) for k in FMA
                                                if ops[k])
-              + "  (%.0f issue slots)" % slots)
+              + "  (%.0f IMAD slots = %.1f per butterfly, kernel text)"
+              % (slots, slots / bfly))
         alu = ("IADD3", "SEL", "LOP3", "LEA", "SHF", "ISETP", "PLOP3", "MOV")
         print("   ALU pipe:      " + ", ".join("%s %d" % (k, ops[k]) for k in alu
                                                if ops[k]))
