@@ -28,7 +28,7 @@ CU_SRCS := $(SRC_DIR)/device.cu $(SRC_DIR)/vector.cu \
            $(SRC_DIR)/kernels_elem.cu $(SRC_DIR)/kernels_ntt.cu \
            $(SRC_DIR)/tables_device.cu $(SRC_DIR)/probe.cu \
            $(SRC_DIR)/kernels_ntt_cluster.cu $(SRC_DIR)/kernels_ntt_tma.cu \
-           $(SRC_DIR)/kernels_ntt_small.cu
+           $(SRC_DIR)/kernels_ntt_small.cu $(SRC_DIR)/hostcopy.cu
 C_SRCS  := $(SRC_DIR)/numbers.c $(SRC_DIR)/ntt_tables.c
 OBJS    := $(CU_SRCS:$(SRC_DIR)/%.cu=$(OBJ_DIR)/%.o) \
            $(C_SRCS:$(SRC_DIR)/%.c=$(OBJ_DIR)/%.o)

@@ -524,7 +524,9 @@ def run_native_arm(args):
                 step_resident()
             ctx.sync()
     barrier()
+    lazy0 = ctx.lazy_forwards
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    lazy_stores = ctx.lazy_forwards - lazy0
     ms_per_step = ms_total / args.steps
     clocks = sampler.window(*timed_window) if rank == 0 else None
     # the sustained figure: the same step for at least SUSTAINED_SECONDS,
@@ -724,6 +726,12 @@ def run_native_arm(args):
                         "N = 1, the Python loop over all ranks otherwise"},
             # whole job: every rank launches the same kernels on its shard
             "gpu_launches": launches * world,
+            # forward transforms (warm-up and timed steps of this rank) whose
+            # results only the in-place inverse transform after them read, and
+            # which therefore stored residues in [0,3q) instead of [0,q)
+            # (vector.cu, held forward transform; $VKHEL_LAZY_FORWARD=0: none).
+            # `checks` reads the forward transform through the API: canonical.
+            "lazy_forward_stores": lazy_stores,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak,

@@ -53,6 +53,7 @@ struct device_ctx {
 	 * not join. */
 	int split_active, split_hold, split_by_limb;
 	int in_slices;       /* kernels being launched belong to a sliced transform */
+	int lazy_out;        /* the forward transform being launched stores lazy values */
 	const void *split_dst;
 	size_t split_bytes;
 	uint64_t split_per, split_units;
@@ -82,6 +83,7 @@ struct device_ctx {
 	uint64_t pinned_seq; /* counter behind pinned_slot.released */
 	void *readahead;     /* results of the last recorded batch, for map() (opaque, C++) */
 	uint64_t readahead_hits;   /* maps served from a copy started before they were called */
+	uint64_t lazy_forwards;    /* held forward transforms launched with lazy stores */
 };
 
 void device_ctx_init(struct device_ctx *dev, int device);

@@ -60,6 +60,10 @@ void vkhel_vector_map_range(struct vkhel_vector *, void **mem,
  * map of a vector that a recorded batch of transforms produced also starts the
  * copies of the next vectors of that batch (vector.cu, read-ahead) */
 uint64_t vkhel_ctx_readahead_hits(const struct vkhel_ctx *);
+/* batched forward transforms that were followed at once by the in-place
+ * inverse transform of their result and therefore stored lazy residues the
+ * inverse overwrote (vector.cu, held forward transform); does not flush */
+uint64_t vkhel_ctx_lazy_forwards(const struct vkhel_ctx *);
 /* enqueue copies of `count` elements starting at element `offset`; the host
  * buffer must stay valid until vkhel_ctx_sync / map / destroy */
 void vkhel_vector_upload(struct vkhel_vector *, const uint64_t *src,

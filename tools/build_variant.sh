@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; defs=$2
 out=build/variants; mkdir -p $out/obj_$name
-for f in device vector kernels_elem kernels_ntt kernels_ntt_cluster kernels_ntt_tma kernels_ntt_small tables_device probe; do
+for f in device vector kernels_elem kernels_ntt kernels_ntt_cluster kernels_ntt_tma kernels_ntt_small tables_device probe hostcopy; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC -Iinclude -Iinclude/vkhel -Ivkhel_b200/csrc $defs \
     -c vkhel_b200/csrc/$f.cu -o $out/obj_$name/$f.o &

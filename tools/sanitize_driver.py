@@ -150,11 +150,16 @@ def main():
     x = np.concatenate([rng.integers(0, primes[p % limbs], n, dtype=np.uint64)
                         for p in range(limbs * batch)])
     a, b = ctx.from_host(x), ctx.vector(x.size)
-    for _ in range(2):
+    for _ in range(3):
         ctx.forward_transform_rns(a, b, tabs, batch)
         ctx.inverse_transform_rns(b, b, tabs, batch)
+    # (the second and third forward transform were held and stored lazily)
+    assert ctx.lazy_forwards == 2 or os.environ.get("VKHEL_LAZY_FORWARD") == "0"
     ctx.elemgtadd(b, b, 0, 0)
     assert np.array_equal(b.to_host(), x)
+    ctx.forward_transform_rns(a, b, tabs, batch)      # held, then read
+    assert np.array_equal(b.to_host()[:n],
+                          oracle.forward(x[:n], oracle.Tables(n, primes[0], tabs[0].w)))
     a.destroy(), b.destroy()
     for t4 in tabs:
         t4.destroy()

@@ -59,6 +59,7 @@ SIGNATURES = {
     "vkhel_vector_device_ptr": (_vp, [_vp]),
     "vkhel_vector_map_range": (None, [_vp, ctypes.POINTER(_vp), _u64, _u64]),
     "vkhel_ctx_readahead_hits": (_u64, [_vp]),
+    "vkhel_ctx_lazy_forwards": (_u64, [_vp]),
     "vkhel_vector_upload": (None, [_vp, _vp, _u64, _u64]),
     "vkhel_vector_download": (None, [_vp, _vp, _u64, _u64]),
     "vkhel_vector_copy_peer": (None, [_vp, _u64, _vp, _u64, _u64]),
@@ -323,6 +324,12 @@ class Context:
     def fused_products(self):
         """elemmul calls that were fused into the inverse transform after them"""
         return int(lib().vkhel_ctx_fused_products(self.handle))
+
+    @property
+    def lazy_forwards(self):
+        """batched forward transforms that stored lazy residues for the
+        in-place inverse transform that followed them at once"""
+        return int(lib().vkhel_ctx_lazy_forwards(self.handle))
 
     @property
     def readahead_hits(self):

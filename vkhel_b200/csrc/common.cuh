@@ -78,6 +78,8 @@ extern "C" void *pinned_acquire(struct vkhel_ctx *ctx, size_t bytes);
 extern "C" void pinned_release(struct vkhel_ctx *ctx, void *ptr);
 extern "C" void pinned_release_after(struct vkhel_ctx *ctx, void *ptr,
 		void *stream);
+/* memcpy, shared with helper threads from 128 KiB on (hostcopy.cu) */
+extern "C" void host_copy(void *dst, const void *src, size_t bytes);
 /* device pointer to the limb_desc of `ntt` on ctx's device (uploads the
  * mirror on first use) */
 const limb_desc *ntt_tables_device_desc(struct vkhel_ctx *ctx,
@@ -108,7 +110,10 @@ void launch_elemmodbytwo(struct vkhel_ctx *ctx, const u64 *in, u64 *out,
  * polynomial p using descs[p % limbs].  dst may equal src. */
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
-		unsigned log2n, uint64_t q_max);
+		unsigned log2n, uint64_t q_max, bool lazy_out = false);
+/* lazy_out (forward only, where ntt_lazy_forward_supported): dst receives
+ * values in [0,3q) that only the inverse transform's kernels may read */
+bool ntt_lazy_forward_supported(unsigned log2n, uint64_t q_max);
 /* kernel launches of one transform launched by launch_ntt on the fast path */
 unsigned ntt_launches_per_transform(unsigned log2n);
 /* inverse transform of the point-wise product src * src2 (any 64-bit values,
@@ -181,6 +186,8 @@ void launch_ntt_small_products(struct vkhel_ctx *ctx, const small_product *tab,
 /* vector.cu: launch the deferred single-vector transforms of the context (all
  * of them, or only if they use `ntt`) */
 void defer_flush(struct vkhel_ctx *ctx);
+/* only a held forward transform (the RNS plan cache, before it evicts) */
+void defer_flush_held(struct vkhel_ctx *ctx);
 void defer_flush_tables(struct vkhel_ctx *ctx,
 		const struct vkhel_ntt_tables *ntt);
 void defer_destroy(struct vkhel_ctx *ctx);

@@ -267,6 +267,10 @@ extern "C" uint64_t vkhel_ctx_readahead_hits(const struct vkhel_ctx *ctx) {
 	return ctx->dev.readahead_hits;
 }
 
+extern "C" uint64_t vkhel_ctx_lazy_forwards(const struct vkhel_ctx *ctx) {
+	return ctx->dev.lazy_forwards;
+}
+
 extern "C" void vkhel_ctx_flush(struct vkhel_ctx *ctx) {
 	ctx_enter(ctx);
 	defer_flush(ctx);
@@ -615,6 +619,7 @@ const limb_desc *rns_plan_device_descs(struct vkhel_ctx *ctx,
 		}
 	}
 	ctx_enter(ctx);
+	defer_flush_held(ctx);   /* (it may use the plan evicted below) */
 	std::vector<limb_desc> host(limbs);
 	rns_plan plan;
 	for (uint64_t l = 0; l < limbs; l++) {

@@ -331,6 +331,7 @@ struct fast_pass {
 	const u64 *src2;      /* row pass, MUL: second operand of the fused point-wise op */
 	u64 fma_mult;         /* MUL: 0 = product src*src2, else src*fma_mult + src2 */
 	bool mul;             /* the row pass of this transform multiplies while it loads */
+	bool lazy;            /* forward: the row pass stores [0,bq), see LAZY below */
 	u64 *dst;
 	const limb_desc *descs;
 	unsigned limbs;
@@ -457,11 +458,19 @@ struct row_cfg {
  * whole transform) and applies n^-1 in it.  A template parameter rather than
  * a run-time branch per round: with both variants in one kernel ptxas merged
  * their register assignments after every round with some 20 moves each. */
-template <bool INV, int K, int NP, bool MUL, bool APX, bool IND, bool TOP>
+/* LAZY (forward only): the outputs are stored after the first of the three
+ * (exact quotient: two) conditional subtractions, i.e. in [0,bq) -- the range
+ * the inverse transform's butterflies accept -- instead of canonical.  Only for
+ * a forward transform whose very next use is the in-place inverse transform
+ * with the same tables (vector.cu, "held forward transform"): the lazy values
+ * are overwritten before anything else can read them. */
+template <bool INV, int K, int NP, bool MUL, bool APX, bool IND, bool TOP,
+	bool LAZY = false>
 __global__ void __launch_bounds__(FAST_THREADS,
 		NP == 2 ? ROWS_MIN_CTAS_NP2 : ROWS_MIN_CTAS_NP1)
 ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 	static_assert(INV || !TOP, "TOP distinguishes inverse passes only");
+	static_assert(!LAZY || (!INV && !IND), "LAZY: direct forward passes only");
 	using G = tile_geom<K>;
 	using C = row_cfg<K>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -672,7 +681,9 @@ ntt_rows_kernel(const __grid_constant__ fast_pass p) {
 				u64 *dp = (IND ? dbase[pp] : p.dst) + off[pp] + tb_last;
 #pragma unroll
 				for (int e = 0; e < 8; e++) {
-					if (canon) {
+					if (LAZY) {
+						x[pp][e] = csub(x[pp][e], bq);   /* [0,2bq) -> [0,bq) */
+					} else if (canon) {
 						x[pp][e] = tile_canon<INV, APX>(x[pp][e], q, bq);
 					}
 				}
@@ -1313,6 +1324,11 @@ static void run_rows_np(struct vkhel_ctx *ctx, fast_pass p) {
 			: ntt_rows_kernel<INV, K, NP, MUL, APX, false, false>;
 	} else {
 		kernel = ntt_rows_kernel<INV, K, NP, MUL, APX, false, false>;
+		if constexpr (!MUL && NP == 1) {
+			if (p.lazy) {
+				kernel = ntt_rows_kernel<INV, K, NP, false, APX, false, false, true>;
+			}
+		}
 	}
 	launch_fast_optin(ctx, kernel, (unsigned) blocks, FAST_THREADS, smem, p);
 }
@@ -1608,6 +1624,7 @@ static void run_fast(struct vkhel_ctx *ctx, const u64 *src, u64 *dst,
 	p.zero = 0;
 	p.fma_mult = fma_mult;
 	p.mul = false;
+	p.lazy = !INV && ctx->dev.lazy_out && !tab && !inline_tab;
 	p.tab = tab;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -1762,6 +1779,7 @@ static void run_fast_polymul(struct vkhel_ctx *ctx, const u64 *a, const u64 *b,
 	p.zero = 0;
 	p.fma_mult = 0;
 	p.mul = false;
+	p.lazy = false;
 	p.tab = NULL;
 	p.tab_second = 0;
 	p.tab_inline = 0;
@@ -2058,12 +2076,36 @@ static bool run_fast_sliced(struct vkhel_ctx *ctx, bool inverse, bool apx,
 	return true;
 }
 
+/* A forward transform may store lazy values ([0,3q) approximate family,
+ * [0,2q) exact) when the in-place inverse transform with the same tables is
+ * the only thing that will ever read them: both directions must take the
+ * two-pass lazy-butterfly kernels.  $VKHEL_LAZY_FORWARD=0 turns it off. */
+bool ntt_lazy_forward_supported(unsigned log2n, uint64_t q_max) {
+	static const bool off = getenv("VKHEL_FORCE_GENERIC") != NULL
+		|| (getenv("VKHEL_LAZY_FORWARD") && !strcmp(getenv("VKHEL_LAZY_FORWARD"), "0"));
+	if (off || q_max >= (1ull << 62) || log2n < 9 || log2n > 30
+			|| log2n <= single_max_log2n() || ntt_cluster_enabled(log2n)
+			|| only_pass()) {
+		return false;
+	}
+	const fast_plan pl = plan_fast(log2n);
+	return pl.kcol && pl.krow;
+}
+
 void launch_ntt(struct vkhel_ctx *ctx, bool inverse, const u64 *src, u64 *dst,
 		const limb_desc *descs, uint64_t limbs, uint64_t polys,
-		unsigned log2n, uint64_t q_max) {
+		unsigned log2n, uint64_t q_max, bool lazy_out) {
 	VK_REQUIRE(log2n >= 1 && log2n <= 30, "unsupported transform size 2^%u",
 			log2n);
 	VK_REQUIRE(q_max < (1ull << 63), "NTT modulus must be below 2^63");
+	VK_REQUIRE(!lazy_out || (!inverse && ntt_lazy_forward_supported(log2n, q_max)),
+			"internal: lazy forward store of 2^%u points", log2n);
+	/* (read by run_fast; cleared again by whoever set it, below) */
+	struct lazy_scope {
+		struct vkhel_ctx *ctx;
+		~lazy_scope() { ctx->dev.lazy_out = 0; }
+	} scope = { ctx };
+	ctx->dev.lazy_out = lazy_out;
 	const bool strict = q_max >= (1ull << 62);
 	static const bool force_generic = getenv("VKHEL_FORCE_GENERIC") != NULL;
 	if (!strict && log2n >= 3 && !force_generic) {

@@ -190,10 +190,21 @@ __device__ __forceinline__ void tile_round(u64 (&x)[NP][8], int r, int t,
 /* canonical residue of a value at the end of a transform: forward values are
  * below 2*bq, inverse values below bq (bq = 2q exact, 3q approximate); the
  * FOLD_LAST stage leaves [0,2q) in both families */
+/* FWD_LAZY_STORE=1 (timing experiment only, tools/build_variant.sh): forward
+ * transforms store [0,bq) instead of canonical values -- what a "lazy vector"
+ * design would save.  The inverse kernels accept that range, so round trips
+ * stay exact, but forward outputs are no longer the reference's. */
+#ifndef FWD_LAZY_STORE
+#define FWD_LAZY_STORE 0
+#endif
+
 template <bool INV, bool APX, int FOLD = FOLD_LAST>
 __device__ __forceinline__ u64 tile_canon(u64 v, u64 q, u64 bq) {
 	if (!INV) {
 		v = csub(v, bq);        /* [0,2bq) -> [0,bq) */
+		if (FWD_LAZY_STORE) {
+			return v;
+		}
 	}
 	if (APX && (!INV || FOLD == FOLD_TWID)) {
 		v = csub(v, q);         /* [0,3q) -> [0,2q) */

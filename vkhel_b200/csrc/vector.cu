@@ -76,10 +76,29 @@ struct pending_product {
 	uint64_t mod, multiplier;
 };
 
+/* A batched forward transform that has been held back, see "held forward
+ * transform" below */
+struct held_forward {
+	bool active;
+	/* the previous batched forward transform was followed at once by its
+	 * in-place inverse: the next one is held back */
+	bool predicted;
+	const struct vkhel_vector *operand;
+	struct vkhel_vector *result;
+	const limb_desc *descs;
+	uint64_t limbs, polys, q_max;
+	unsigned log2n;
+	/* the last batched forward transform that was launched at once */
+	const void *last_dst;
+	const limb_desc *last_descs;
+	uint64_t last_polys, last_serial;
+};
+
 /* most whole products recorded for one launch (40 bytes of pointers each) */
 #define PRODUCTS_MAX 1024
 
 struct defer_queue {
+	held_forward fwd;
 	pending_product mul;
 	/* ---- recorded whole products (small n, see "recorded whole products") ---- */
 	struct {
@@ -114,6 +133,7 @@ static defer_queue *defer_get(struct vkhel_ctx *ctx) {
 		 * the calling thread last used */
 		enter(ctx);
 		defer_queue *dq = new defer_queue();
+		memset(&dq->fwd, 0, sizeof(dq->fwd));
 		dq->mul.active = false;
 		dq->mul.with_forwards = false;
 		dq->mul.after_items = false;
@@ -413,10 +433,122 @@ static void launch_recorded_inverse_products(struct vkhel_ctx *ctx,
 	dq->inv_product_tables = NULL;
 }
 
+/* ---- held forward transform ---------------------------------------------------------
+ * The reference stores canonical residues after every transform
+ * (nttfwdbutterfly.comp:41-57), and so does every kernel here -- three
+ * conditional subtractions per coefficient at the end of a forward transform
+ * of the approximate-quotient family, 12 of the 171 us of the forward row pass
+ * of the bench workload.  The inverse transform's butterflies, however, accept
+ * [0,3q) as they are, so when a batched forward transform is followed at once
+ * by the in-place inverse transform of its result with the same tables
+ * (forward -> inverse is the reference's headline loop, BASELINE.json), the
+ * forward may store after the first subtraction: the lazy values are
+ * overwritten by the inverse before anything can observe them.
+ *
+ * Which call comes next is only known when it arrives, so the forward transform
+ * is held back (like the recorded product above) and launched by the next use
+ * of the context: lazily by the matching inverse, canonically by anything
+ * else (every entry point passes through defer_flush).  Holding a launch back
+ * delays the GPU if the application computes on the host before its next
+ * call, so a forward transform is only held when the previous one was
+ * followed by its inverse (`predicted`): a loop pays for one canonical
+ * forward, a single call for nothing.  Callers that hold the stream or a
+ * device pointer are never deferred.  $VKHEL_LAZY_FORWARD=0 turns it off. */
+static void launch_held_forward(struct vkhel_ctx *ctx, defer_queue *dq,
+		bool lazy) {
+	held_forward &h = dq->fwd;
+	h.active = false;
+	enter(ctx);
+	/* as sliced_operands below: slices left on the auxiliary streams are
+	 * joined by launch_ntt unless this transform continues them -- which only
+	 * the context's stream could not do for a pending transfer */
+	if (h.operand->xfer_pending || h.result->xfer_pending) {
+		ntt_split_join(ctx);
+	}
+	const u64 *src = dev_u64_nodefer(h.operand);
+	u64 *dst = dev_u64_nodefer(h.result);
+	launch_ntt(ctx, false, src, dst, h.descs, h.limbs, h.polys, h.log2n,
+			h.q_max, lazy);
+	ctx->dev.lazy_forwards += lazy;
+}
+
+/* forward entry points: hold the transform back (true) or let the caller
+ * launch it now */
+static bool hold_forward(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, const limb_desc *descs, uint64_t limbs,
+		uint64_t polys, unsigned log2n, uint64_t q_max) {
+	static const bool off = getenv("VKHEL_NO_DEFER") != NULL;
+	struct vkhel_ctx *ctx = result->ctx;
+	if (off || ctx->dev.stream_exposed || operand->exposed || result->exposed
+			|| !ntt_lazy_forward_supported(log2n, q_max)) {
+		return false;
+	}
+	defer_queue *dq = defer_get(ctx);
+	/* whatever is recorded goes first (an earlier held forward included), the
+	 * slices in flight stay as they are: this transform may continue them */
+	ctx->dev.split_hold = 1;
+	defer_flush(ctx);
+	ctx->dev.split_hold = 0;
+	held_forward &h = dq->fwd;
+	if (!h.predicted) {
+		/* launched by the caller; remembered for the inverse that may follow */
+		h.last_dst = result->device.ptr;
+		h.last_descs = descs;
+		h.last_polys = polys;
+		h.last_serial = ctx->dev.op_serial + 2;   /* after the caller's two fetches */
+		return false;
+	}
+	h.active = true;
+	h.operand = operand;
+	h.result = result;
+	h.descs = descs;
+	h.limbs = limbs;
+	h.polys = polys;
+	h.q_max = q_max;
+	h.log2n = log2n;
+	return true;
+}
+
+/* inverse entry points, before anything else touches the context: launch a
+ * held forward transform lazily if this is its inverse, and learn the pattern */
+static void inverse_follows(const struct vkhel_vector *operand,
+		struct vkhel_vector *result, const limb_desc *descs, uint64_t polys) {
+	defer_queue *dq = (defer_queue *) result->ctx->dev.defer;
+	if (!dq) {
+		return;
+	}
+	held_forward &h = dq->fwd;
+	const bool in_place = operand == result;
+	if (h.active) {
+		if (in_place && h.result == result && h.descs == descs
+				&& h.polys == polys) {
+			launch_held_forward(result->ctx, dq, true);
+		}
+		return;   /* (anything else: defer_flush launches it canonically) */
+	}
+	if (in_place && h.last_dst == result->device.ptr && h.last_descs == descs
+			&& h.last_polys == polys
+			&& h.last_serial == result->ctx->dev.op_serial) {
+		h.predicted = true;
+	}
+	h.last_dst = NULL;
+}
+
+void defer_flush_held(struct vkhel_ctx *ctx) {
+	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	if (dq && dq->fwd.active) {
+		dq->fwd.predicted = false;
+		launch_held_forward(ctx, dq, false);
+	}
+}
+
 void defer_flush(struct vkhel_ctx *ctx) {
 	/* everything that is about to use the context's stream comes through
 	 * here: slices still on the auxiliary stream are joined first */
 	defer_queue *dq = (defer_queue *) ctx->dev.defer;
+	/* a held forward transform that was not followed by its inverse: launched
+	 * as if it had never been held, and the next one is not held */
+	defer_flush_held(ctx);
 	const bool recorded = dq && (!dq->items.empty() || !dq->products.empty()
 			|| !dq->inv_products.empty());
 	/* (a batched transform that may continue the slices holds the join back
@@ -463,7 +595,7 @@ void defer_flush_tables(struct vkhel_ctx *ctx,
 	if (!dq) {
 		return;
 	}
-	if (dq->product_tables == ntt || dq->inv_product_tables == ntt
+	if (dq->fwd.active || dq->product_tables == ntt || dq->inv_product_tables == ntt
 			|| (dq->triple.active && dq->triple.ntt == ntt)
 			|| (dq->mul.active && dq->mul.after_items && dq->mul.ntt == ntt)) {
 		defer_flush(ctx);
@@ -821,7 +953,7 @@ extern "C" void vkhel_vector_copy_from_host(struct vkhel_vector *vec,
 	while (left) {
 		const size_t piece = left < STAGE_CHUNK_BYTES ? left : STAGE_CHUNK_BYTES;
 		void *stage = pinned_acquire(ctx, piece);
-		memcpy(stage, src, piece);
+		host_copy(stage, src, piece);
 		CUDA_CHECK(cudaMemcpyAsync(dst, stage, piece, cudaMemcpyHostToDevice,
 					ctx_stream(ctx)));
 		pinned_release_after(ctx, stage, ctx_stream(ctx));
@@ -1215,8 +1347,12 @@ extern "C" void vkhel_vector_forward_transform_batch(
 	if (ntt->n < 2 || batch == 0) {
 		return; /* no stages: the reference leaves result untouched */
 	}
-	launch_ntt(ctx, false, dev_u64(operand), dev_u64(result),
-			ntt_tables_device_desc(ctx, ntt), 1, batch,
+	const limb_desc *desc = ntt_tables_device_desc(ctx, ntt);
+	if (batch > 1 && hold_forward(operand, result, desc, 1, batch,
+				(unsigned) ntt->log2n, ntt->q)) {
+		return;
+	}
+	launch_ntt(ctx, false, dev_u64(operand), dev_u64(result), desc, 1, batch,
 			(unsigned) ntt->log2n, ntt->q);
 }
 
@@ -1236,8 +1372,9 @@ extern "C" void vkhel_vector_inverse_transform_batch(
 				ntt->inv_n, ntt->q);
 		return;
 	}
-	launch_ntt(ctx, true, dev_u64(operand), dev_u64(result),
-			ntt_tables_device_desc(ctx, ntt), 1, batch,
+	const limb_desc *desc = ntt_tables_device_desc(ctx, ntt);
+	inverse_follows(operand, result, desc, batch);
+	launch_ntt(ctx, true, dev_u64(operand), dev_u64(result), desc, 1, batch,
 			(unsigned) ntt->log2n, ntt->q);
 }
 
@@ -1329,6 +1466,10 @@ extern "C" void vkhel_vector_forward_transform_rns(
 	if (ntt[0]->n < 2 || batch == 0) {
 		return;
 	}
+	if (hold_forward(operand, result, descs, limbs, limbs * batch,
+				(unsigned) ntt[0]->log2n, q_max)) {
+		return;
+	}
 	const u64 *src;
 	u64 *dst;
 	sliced_operands(operand, result, &src, &dst);
@@ -1347,6 +1488,7 @@ extern "C" void vkhel_vector_inverse_transform_rns(
 	if (batch == 0) {
 		return;
 	}
+	inverse_follows(operand, result, descs, limbs * batch);
 	const u64 *src;
 	u64 *dst;
 	sliced_operands(operand, result, &src, &dst);
