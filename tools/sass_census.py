@@ -22,8 +22,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNELS = [
     ("forward columns  <0,8,4,2,apx>", "ntt_cols_kernelILb0ELi8ELi4ELi2ELb1ELb0ELb0E", 64),
-    ("forward rows     <0,8,1,apx>", "ntt_rows_kernelILb0ELi8ELi1ELb0ELb1ELb0ELb0E", 32),
-    ("inverse rows     <1,8,1,apx>", "ntt_rows_kernelILb1ELi8ELi1ELb0ELb1ELb0ELb0E", 32),
+    ("forward rows     <0,8,1,apx>", "ntt_rows_kernelILb0ELi8ELi1ELb0ELb1ELb0ELb0ELb0E", 32),
+    ("forward rows     <0,8,1,apx,lazy> (held forward transform)", "ntt_rows_kernelILb0ELi8ELi1ELb0ELb1ELb0ELb0ELb1E", 32),
+    ("inverse rows     <1,8,1,apx>", "ntt_rows_kernelILb1ELi8ELi1ELb0ELb1ELb0ELb0ELb0E", 32),
     ("inverse columns  <1,8,4,2,apx,top>", "ntt_cols_kernelILb1ELi8ELi4ELi2ELb1ELb0ELb1E", 64),
 ]
 FMA = ("IMAD.WIDE", "IMAD.HI", "IMAD", "IMAD.X", "IMAD.MOV", "IMAD.IADD",
