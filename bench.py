@@ -567,29 +567,69 @@ def run_native_arm(args):
     ms_inv, _ = timed(inv_only, args.steps, 1)
 
     host_out.array[:] = 0
-    e2e_steps = max(2, min(args.steps, 20))
-    ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
-    ok = ok and bool(np.array_equal(host_out.array, host_in.array))
+    # (at N > 1 a step is a fraction of the one-GPU step: more of them, so that
+    # filling and draining the pipeline weighs the same at every N)
+    e2e_steps = max(2, min(args.steps, 20) * min(world, 4))
 
-    # the box's own host <-> device bandwidth, all ranks copying at once,
-    # without the library (tools/pcie_probe.py: plain cudaMemcpyAsync)
+    # The box's own host <-> device bandwidth, all ranks copying at once,
+    # without the library (tools/pcie_probe.py: plain cudaMemcpyAsync).  The
+    # pool's hosts are shared and their PCIe throughput moves by tens of
+    # percent within seconds, so the probe runs right before and right after
+    # the end-to-end segments, and the end-to-end figure is the median of three
+    # segments of e2e_steps steps.
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    try:
-        import pcie_probe
-        pcie = pcie_probe.measure(local_rank, mib=128, reps=4, barrier=barrier)
-        both = sum_over_ranks(pcie["both_each_GBps"])
+
+    def probe_ceiling():
+        try:
+            import pcie_probe
+            pcie = pcie_probe.measure(local_rank, mib=128, reps=4,
+                                      barrier=barrier)
+            piped = pcie_probe.measure_pipelined(
+                local_rank, chunk_elems * 8, chunks=E2E_CHUNKS,
+                steps=e2e_steps, barrier=barrier)
+            vals = [pcie["both_each_GBps"], pcie["h2d_alone_GBps"],
+                    pcie["d2h_alone_GBps"], piped["pipelined_each_GBps"]]
+            err = None
+        except Exception as exc:    # noqa: BLE001 (probe is best effort)
+            vals, err = [0.0] * 4, str(exc)[:120]
+        return [sum_over_ranks(v) for v in vals], err
+
+    before, err0 = probe_ceiling()
+    e2e_segments = []
+    for seg in range(3):
+        ms_seg, _ = timed(step_e2e, e2e_steps, 2 if seg == 0 else 0)
+        e2e_segments.append(ms_seg)
+    ms_e2e = sorted(e2e_segments)[1]
+    ok = ok and bool(np.array_equal(host_out.array, host_in.array))
+    after, err1 = probe_ceiling()
+    if err0 or err1 or not before[0] or not after[0]:
+        ceiling = {"value": None, "unit": "NTT/s", "error": err0 or err1}
+    else:
+        both, h2d_alone, d2h_alone, piped_all = [
+            (x + y) / 2 for x, y in zip(before, after)]
+        per_gbps = 1e9 / (256 * 1024)
         ceiling = {
-            "value": both * 1e9 / (256 * 1024), "unit": "NTT/s",
+            "value": both * per_gbps, "unit": "NTT/s",
             "aggregate_both_directions_each_GBps": both,
-            "aggregate_h2d_alone_GBps": sum_over_ranks(pcie["h2d_alone_GBps"]),
-            "aggregate_d2h_alone_GBps": sum_over_ranks(pcie["d2h_alone_GBps"]),
+            "aggregate_h2d_alone_GBps": h2d_alone,
+            "aggregate_d2h_alone_GBps": d2h_alone,
+            "before_and_after_the_e2e_run": [before[0] * per_gbps,
+                                             after[0] * per_gbps],
             "how": "tools/pcie_probe.py: cudaMemcpyAsync of 128 MiB pinned "
                    "buffers on every rank at once, no library; one NTT moves "
-                   "256 KiB each way while both directions are busy",
+                   "256 KiB each way while both directions are busy; mean of "
+                   "a probe before and a probe after the e2e segments",
+            # the same copies as the e2e path issues (slice size, slices per
+            # step, each download behind its upload, two buffer sets), without
+            # the library and without kernels
+            "pipelined": {
+                "value": piped_all * per_gbps, "unit": "NTT/s",
+                "aggregate_each_GBps": piped_all,
+                "before_and_after_the_e2e_run": [before[3] * per_gbps,
+                                                 after[3] * per_gbps],
+                "slice_mib": chunk_elems * 8 / 2 ** 20,
+                "slices_per_step": E2E_CHUNKS, "steps": e2e_steps},
         }
-    except Exception as err:    # noqa: BLE001 (probe is best effort)
-        sum_over_ranks(0.0), sum_over_ranks(0.0), sum_over_ranks(0.0)
-        ceiling = {"value": None, "unit": "NTT/s", "error": str(err)[:120]}
 
     # the weak-scaling figure: every rank runs the whole one-GPU workload
     weak = None
@@ -700,8 +740,14 @@ def run_native_arm(args):
                     "h2d_bytes_per_step": POLYS * N * 8,
                     "d2h_bytes_per_step": POLYS * N * 8,
                     "steps": e2e_steps,
+                    "segments": [ntts_per_step / (m / e2e_steps * 1e-3)
+                                 for m in e2e_segments],
+                    "value_is": "median of three segments of `steps` steps",
                     "frac_of_ceiling": (e2e_value / ceiling["value"]
                                         if ceiling.get("value") else None),
+                    "frac_of_pipelined_ceiling": (
+                        e2e_value / ceiling["pipelined"]["value"]
+                        if ceiling.get("pipelined") else None),
                     "path": "per slice of 4 batch entries: vkhel_vector_upload "
                             "(pinned) -> forward_transform_rns -> "
                             "inverse_transform_rns -> vkhel_vector_download;"

@@ -91,12 +91,78 @@ def measure(device, mib=256, reps=6, barrier=None, write_combined=False):
     return out
 
 
+def measure_pipelined(device, chunk_bytes, chunks=4, steps=20, barrier=None):
+    """GB/s per direction of the copy pattern of bench.py's e2e path WITHOUT
+    the library and without kernels: per step `chunks` slices of `chunk_bytes`,
+    each uploaded into its own device buffer and downloaded again as soon as
+    its upload has ended; two sets of device buffers used alternately, an
+    upload into a buffer waits for the download that last read it.  The figure
+    a pipeline with these dependencies can reach, as opposed to two independent
+    streams of 128 MiB copies (measure)."""
+    from cuda.bindings import runtime as rt
+    _check(rt.cudaSetDevice(device))
+    total = chunk_bytes * chunks
+    hin = _check(rt.cudaHostAlloc(total, rt.cudaHostAllocDefault))
+    hout = _check(rt.cudaHostAlloc(total, rt.cudaHostAllocDefault))
+    dev = [[_check(rt.cudaMalloc(chunk_bytes)) for _ in range(chunks)]
+           for _ in range(2)]
+    s_up = _check(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+    s_down = _check(rt.cudaStreamCreateWithFlags(rt.cudaStreamNonBlocking))
+    up_done = [[_check(rt.cudaEventCreateWithFlags(rt.cudaEventDisableTiming))
+                for _ in range(chunks)] for _ in range(2)]
+    down_done = [[_check(rt.cudaEventCreateWithFlags(rt.cudaEventDisableTiming))
+                  for _ in range(chunks)] for _ in range(2)]
+    e0, e1, ej = (_check(rt.cudaEventCreate()) for _ in range(3))
+    h2d = rt.cudaMemcpyKind.cudaMemcpyHostToDevice
+    d2h = rt.cudaMemcpyKind.cudaMemcpyDeviceToHost
+
+    def step(k, first):
+        cur = k & 1
+        for c in range(chunks):
+            if not first:
+                _check(rt.cudaStreamWaitEvent(s_up, down_done[cur][c], 0))
+            _check(rt.cudaMemcpyAsync(dev[cur][c], hin + c * chunk_bytes,
+                                      chunk_bytes, h2d, s_up))
+            _check(rt.cudaEventRecord(up_done[cur][c], s_up))
+            _check(rt.cudaStreamWaitEvent(s_down, up_done[cur][c], 0))
+            _check(rt.cudaMemcpyAsync(hout + c * chunk_bytes, dev[cur][c],
+                                      chunk_bytes, d2h, s_down))
+            _check(rt.cudaEventRecord(down_done[cur][c], s_down))
+
+    for k in range(2):                       # warm-up, fills both sets
+        step(k, True)
+    _check(rt.cudaDeviceSynchronize())
+    if barrier is not None:
+        barrier()
+    _check(rt.cudaEventRecord(e0, s_up))
+    _check(rt.cudaStreamWaitEvent(s_down, e0, 0))
+    for k in range(steps):
+        step(k, False)
+    _check(rt.cudaEventRecord(ej, s_down))
+    _check(rt.cudaStreamWaitEvent(s_up, ej, 0))
+    _check(rt.cudaEventRecord(e1, s_up))
+    _check(rt.cudaEventSynchronize(e1))
+    ms = _check(rt.cudaEventElapsedTime(e0, e1))
+    for ev in [e0, e1, ej] + sum(up_done, []) + sum(down_done, []):
+        _check(rt.cudaEventDestroy(ev))
+    _check(rt.cudaStreamDestroy(s_up))
+    _check(rt.cudaStreamDestroy(s_down))
+    for buf in sum(dev, []):
+        _check(rt.cudaFree(buf))
+    _check(rt.cudaFreeHost(hin))
+    _check(rt.cudaFreeHost(hout))
+    return {"pipelined_each_GBps": total * steps / (ms * 1e-3) / 1e9,
+            "chunk_mib": chunk_bytes / MIB, "chunks_per_step": chunks,
+            "steps": steps}
+
+
 def summarise(per_rank):
     """aggregate over the ranks that copied concurrently; the e2e ceiling in
     NTT/s at n = 2^16: 512 KiB in and 512 KiB out per NTT pair, i.e. 256 KiB
     each way per NTT while both directions are active"""
     total = {k: sum(r[k] for r in per_rank)
-             for k in ("h2d_alone_GBps", "d2h_alone_GBps", "both_each_GBps")}
+             for k in ("h2d_alone_GBps", "d2h_alone_GBps", "both_each_GBps",
+                       "pipelined_each_GBps") if k in per_rank[0]}
     total["n_gpus"] = len(per_rank)
     total["e2e_ceiling_ntt_per_s"] = total["both_each_GBps"] * 1e9 / (256 * 1024)
     return total
@@ -113,6 +179,10 @@ def main():
         dist.init_process_group("gloo")
         barrier = dist.barrier
     mine = measure(local_rank, barrier=barrier, write_combined=wc)
+    # the e2e path's slices at this number of GPUs (bench.py: 32/world limbs x
+    # 4 batch entries of 512 KiB per slice, 4 slices per step)
+    mine.update(measure_pipelined(local_rank, (32 // world) * 4 * 512 * 1024,
+                                  barrier=barrier))
     if dist is not None:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
