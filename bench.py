@@ -228,6 +228,20 @@ def make_inputs(primes, lo, hi):
     return out
 
 
+def make_inputs_for(primes, limb_list, b0, b1):
+    """[b1 - b0][limb_list][N]: the same polynomials as make_inputs, for any
+    limbs and batch range (the end-to-end path's plan)"""
+    from vkhel_b200 import params
+    out = np.empty((b1 - b0) * len(limb_list) * N, np.uint64)
+    p = 0
+    for b in range(b0, b1):
+        for l in limb_list:
+            out[p * N:(p + 1) * N] = params.xorshift64_stream(
+                poly_seed(b, l), N, primes[l])
+            p += 1
+    return out
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -465,25 +479,9 @@ def run_native_arm(args):
         ctx.forward_transform_rns(data, work, tables, BATCH)
         ctx.inverse_transform_rns(work, work, tables, BATCH)
 
-    # end-to-end path: the shard moves in E2E_CHUNKS slices of whole batch
-    # entries, each slice on its own device vector, two sets of slices used
-    # alternately: upload (H2D copy stream), both transforms (compute stream)
-    # and download (D2H copy stream) of different slices overlap.
+    # equal-shard slice of the end-to-end path (the ceiling probes copy these)
     chunk_batch = BATCH // E2E_CHUNKS
     chunk_elems = chunk_batch * own * N
-    slices = [[ctx.vector(chunk_elems, zero=False) for _ in range(E2E_CHUNKS)]
-              for _ in range(2)]
-    e2e_state = {"step": 0}
-
-    def step_e2e():
-        cur = slices[e2e_state["step"] & 1]
-        e2e_state["step"] += 1
-        for c, v in enumerate(cur):
-            v.upload(host_in, count=chunk_elems, host_offset=c * chunk_elems)
-            ctx.forward_transform_rns(v, v, tables, chunk_batch)
-            ctx.inverse_transform_rns(v, v, tables, chunk_batch)
-            v.download(host_out, count=chunk_elems,
-                       host_offset=c * chunk_elems)
 
     timer = ctx.timer()
     timed_window = [0.0, 0.0]   # host clock around the last timed region
@@ -592,21 +590,65 @@ def run_native_arm(args):
             err = None
         except Exception as exc:    # noqa: BLE001 (probe is best effort)
             vals, err = [0.0] * 4, str(exc)[:120]
-        return [sum_over_ranks(v) for v in vals], err
+        # (the slowest rank's share: with equal shards and the clock stopped
+        # by the last rank, world x this is what the job can reach)
+        slowest = -max_over_ranks(-vals[3])
+        return ([sum_over_ranks(v) for v in vals] + [slowest * world, vals[3]],
+                err)
 
     before, err0 = probe_ceiling()
+
+    # End-to-end path.  Who moves what follows the rates just measured
+    # (shard.e2e_plan): at N = 1 the whole workload; at N > 1 pairs of ranks,
+    # slowest with fastest, share the limbs of their two shards and split the
+    # batch entries in proportion to their rates, because with equal shards
+    # the job ends with the slowest rank (`e2e_ceiling.equal_shards`).  A
+    # rank's part moves in up to E2E_CHUNKS slices of whole batch entries, each
+    # slice on its own device vector, two sets of slices used alternately:
+    # upload (H2D copy stream), both transforms (compute stream) and download
+    # (D2H copy stream) of different slices overlap.
+    rates = [0.0] * world
+    rates[rank] = before[5]
+    rates = [sum_over_ranks(x) for x in rates] if world > 1 else rates
+    e2e_limbs, e2e_b0, e2e_b1 = shard.e2e_plan(rates, LIMBS, BATCH)[rank]
+    e2e_batches = [b1 - b0 for _, b0, b1 in shard.e2e_plan(rates, LIMBS, BATCH)]
+    own_tables = dict(zip(range(lo, hi), tables))
+    extra_tables = {l: vk.NttTables(N, primes[l], params.find_psi(N, primes[l]),
+                                    ctx=ctx)
+                    for l in e2e_limbs if l not in own_tables}
+    e2e_tables = [own_tables.get(l) or extra_tables[l] for l in e2e_limbs]
+    e2e_sizes = shard.chunk_sizes(e2e_b1 - e2e_b0, E2E_CHUNKS)
+    e2e_in = vk.host_alloc((e2e_b1 - e2e_b0) * len(e2e_limbs) * N)
+    e2e_out = vk.host_alloc((e2e_b1 - e2e_b0) * len(e2e_limbs) * N)
+    e2e_in.array[:] = make_inputs_for(primes, e2e_limbs, e2e_b0, e2e_b1)
+    e2e_out.array[:] = 0
+    slices = [[ctx.vector(size * len(e2e_limbs) * N, zero=False)
+               for size in e2e_sizes] for _ in range(2)]
+    e2e_state = {"step": 0}
+
+    def step_e2e():
+        cur = slices[e2e_state["step"] & 1]
+        e2e_state["step"] += 1
+        offset = 0
+        for v, size in zip(cur, e2e_sizes):
+            v.upload(e2e_in, count=v.length, host_offset=offset)
+            ctx.forward_transform_rns(v, v, e2e_tables, size)
+            ctx.inverse_transform_rns(v, v, e2e_tables, size)
+            v.download(e2e_out, count=v.length, host_offset=offset)
+            offset += v.length
+
     e2e_segments = []
     for seg in range(3):
         ms_seg, _ = timed(step_e2e, e2e_steps, 2 if seg == 0 else 0)
         e2e_segments.append(ms_seg)
     ms_e2e = sorted(e2e_segments)[1]
-    ok = ok and bool(np.array_equal(host_out.array, host_in.array))
+    ok = ok and bool(np.array_equal(e2e_out.array, e2e_in.array))
     after, err1 = probe_ceiling()
     if err0 or err1 or not before[0] or not after[0]:
         ceiling = {"value": None, "unit": "NTT/s", "error": err0 or err1}
     else:
-        both, h2d_alone, d2h_alone, piped_all = [
-            (x + y) / 2 for x, y in zip(before, after)]
+        both, h2d_alone, d2h_alone, piped_all, piped_equal = [
+            (x + y) / 2 for x, y in zip(before[:5], after[:5])]
         per_gbps = 1e9 / (256 * 1024)
         ceiling = {
             "value": both * per_gbps, "unit": "NTT/s",
@@ -629,6 +671,12 @@ def run_native_arm(args):
                                                  after[3] * per_gbps],
                 "slice_mib": chunk_elems * 8 / 2 ** 20,
                 "slices_per_step": E2E_CHUNKS, "steps": e2e_steps},
+            # N x the slowest rank's pipelined rate: the limb shards are equal
+            # and the e2e clock stops with the last rank, so a box whose GPUs
+            # get unequal shares of the host fabric (this pool at N = 8: 8.4
+            # GB/s each way for GPUs 0-3, 11.9 for GPUs 4-7) caps the job here
+            "equal_shards": {"value": piped_equal * per_gbps, "unit": "NTT/s",
+                             "aggregate_each_GBps": piped_equal},
         }
 
     # the weak-scaling figure: every rank runs the whole one-GPU workload
@@ -748,7 +796,19 @@ def run_native_arm(args):
                     "frac_of_pipelined_ceiling": (
                         e2e_value / ceiling["pipelined"]["value"]
                         if ceiling.get("pipelined") else None),
-                    "path": "per slice of 4 batch entries: vkhel_vector_upload "
+                    "frac_of_equal_shards_ceiling": (
+                        e2e_value / ceiling["equal_shards"]["value"]
+                        if ceiling.get("equal_shards") else None),
+                    "sharding": ("one GPU: all limbs, all batch entries"
+                                 if world == 1 else
+                                 "pairs of ranks (slowest with fastest measured "
+                                 "host <-> device rate) share the limbs of "
+                                 "their two shards and split the 16 batch "
+                                 "entries in proportion to their rates"),
+                    "batch_entries_per_rank": e2e_batches,
+                    "rates_GBps_per_rank": rates,
+                    "path": "per slice of whole batch entries (up to 4 slices "
+                            "per step): vkhel_vector_upload "
                             "(pinned) -> forward_transform_rns -> "
                             "inverse_transform_rns -> vkhel_vector_download;"
                             " copies on the context's H2D/D2H streams "
@@ -815,6 +875,10 @@ def run_native_arm(args):
         t.destroy()
     host_in.free()
     host_out.free()
+    e2e_in.free()
+    e2e_out.free()
+    for t in extra_tables.values():
+        t.destroy()
     ctx.destroy()
     if dist is not None:
         dist.destroy_process_group()

@@ -82,3 +82,45 @@ def test_two_rank_gloo_limb_shard_and_gather():
     for rank, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, out
         assert "rank %d ok" % rank in out
+
+
+def test_e2e_plan_covers_every_polynomial_once_and_follows_the_rates():
+    """bench.py's end-to-end sharding (shard.e2e_plan): whatever the measured
+    rates, every (limb, batch entry) is moved by exactly one rank; a pair's
+    batch split follows its two rates; equal rates give equal work."""
+    from vkhel_b200 import shard
+    limbs, batch = 32, 16
+    cases = {
+        1: [[48.0]],
+        2: [[42.5, 31.1], [40.0, 40.0], [0.0, 0.0]],
+        4: [[17.5, 17.5, 23.5, 23.5], [20.0] * 4],
+        8: [[8.0] * 4 + [11.3] * 4, [11.3, 8.0] * 4, [10.0] * 8,
+            [1.0, 100.0] + [10.0] * 6],
+    }
+    for world, rate_sets in cases.items():
+        for rates in rate_sets:
+            plan = shard.e2e_plan(rates, limbs, batch)
+            seen = {}
+            for r, (ls, b0, b1) in enumerate(plan):
+                assert 0 <= b0 < b1 <= batch and ls == sorted(set(ls))
+                for l in ls:
+                    for b in range(b0, b1):
+                        assert (l, b) not in seen, (world, rates, l, b)
+                        seen[(l, b)] = r
+            assert len(seen) == limbs * batch
+            work = [len(ls) * (b1 - b0) for ls, b0, b1 in plan]
+            if len(set(rates)) == 1:
+                assert set(work) == {limbs * batch // world}
+            elif world > 1:
+                # the faster rank of the extreme pair moves more
+                slow = min(range(world), key=lambda r: (rates[r], r))
+                fast = max(range(world), key=lambda r: (rates[r], -r))
+                assert work[fast] >= work[slow]
+    # 8.0 against 11.3 GB/s: 7 and 9 batch entries of the pair's 8 limbs
+    plan = shard.e2e_plan([8.0] * 4 + [11.3] * 4, limbs, batch)
+    assert [b1 - b0 for _, b0, b1 in plan] == [7] * 4 + [9] * 4
+    assert all(len(ls) == 8 for ls, _, _ in plan)
+    assert shard.chunk_sizes(7, 4) == [2, 2, 2, 1]
+    assert shard.chunk_sizes(9, 4) == [3, 2, 2, 2]
+    assert shard.chunk_sizes(16, 4) == [4, 4, 4, 4]
+    assert shard.chunk_sizes(2, 4) == [1, 1]

@@ -29,6 +29,45 @@ def batch_shard(batch, world, rank):
     return split_range(batch, world, rank)
 
 
+def e2e_plan(rates, limbs, batch):
+    """Who moves what in the end-to-end (host -> GPU -> host) path.
+
+    `rates[r]` is rank r's measured host <-> device rate while all ranks copy.
+    With equal limb shards the job ends with the slowest rank, and on a box
+    whose GPUs get unequal shares of the host fabric that wastes the others'
+    bandwidth.  So ranks are paired, slowest with fastest: a pair shares the
+    limbs of both equal shards and splits the batch entries in proportion to
+    the two rates (at least one entry each; equal rates give equal halves, i.e.
+    as many polynomials per rank as the equal limb shards).
+
+    Returns, for every rank, (limb list, batch begin, batch end).  One rank, or
+    an odd number of ranks: the plain limb shards over the whole batch."""
+    world = len(rates)
+    if world == 1 or world % 2 or batch < 2:
+        return [(list(range(*limb_shard(limbs, world, r))), 0, batch)
+                for r in range(world)]
+    order = sorted(range(world), key=lambda r: (rates[r], r))
+    plan = [None] * world
+    for i in range(world // 2):
+        slow, fast = order[i], order[world - 1 - i]
+        both = sorted(list(range(*limb_shard(limbs, world, slow)))
+                      + list(range(*limb_shard(limbs, world, fast))))
+        total = rates[slow] + rates[fast]
+        share = rates[slow] / total if total > 0 else 0.5
+        cut = min(batch - 1, max(1, int(round(batch * share))))
+        plan[slow] = (both, 0, cut)
+        plan[fast] = (both, cut, batch)
+    return plan
+
+
+def chunk_sizes(count, chunks):
+    """`count` batch entries cut into at most `chunks` slices of whole entries,
+    sizes differing by at most one, larger ones first"""
+    chunks = max(1, min(chunks, count))
+    base, extra = divmod(count, chunks)
+    return [base + (1 if c < extra else 0) for c in range(chunks)]
+
+
 def gather_limb_sharded(local, limbs, n, batch, dist):
     """Optional result gather (NOT on the hot path): every rank holds
     [batch][own limbs][n]; returns the full [batch][limbs][n] array on every
