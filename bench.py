@@ -580,11 +580,14 @@ def run_native_arm(args):
     def probe_ceiling():
         try:
             import pcie_probe
-            pcie = pcie_probe.measure(local_rank, mib=128, reps=4,
-                                      barrier=barrier)
+            # at N > 1 for a fixed time, not a fixed amount: every rank copies
+            # against all the others for the whole measurement (pcie_probe)
+            secs = 0.3 if world > 1 else None
+            pcie = pcie_probe.measure(local_rank, mib=32 if secs else 128,
+                                      reps=4, barrier=barrier, seconds=secs)
             piped = pcie_probe.measure_pipelined(
                 local_rank, chunk_elems * 8, chunks=E2E_CHUNKS,
-                steps=e2e_steps, barrier=barrier)
+                steps=e2e_steps, barrier=barrier, seconds=secs)
             vals = [pcie["both_each_GBps"], pcie["h2d_alone_GBps"],
                     pcie["d2h_alone_GBps"], piped["pipelined_each_GBps"]]
             err = None
@@ -657,10 +660,14 @@ def run_native_arm(args):
             "aggregate_d2h_alone_GBps": d2h_alone,
             "before_and_after_the_e2e_run": [before[0] * per_gbps,
                                              after[0] * per_gbps],
-            "how": "tools/pcie_probe.py: cudaMemcpyAsync of 128 MiB pinned "
-                   "buffers on every rank at once, no library; one NTT moves "
-                   "256 KiB each way while both directions are busy; mean of "
-                   "a probe before and a probe after the e2e segments",
+            "how": "tools/pcie_probe.py: cudaMemcpyAsync of pinned buffers "
+                   "on every rank at once, no library (N = 1: 4 copies of 128 "
+                   "MiB; N > 1: 32 MiB copies for 0.3 s per measurement, so "
+                   "that every rank copies against all the others throughout "
+                   "-- a fixed amount per rank lets the better-connected GPUs "
+                   "finish early and flatters the sum); one NTT moves 256 KiB "
+                   "each way while both directions are busy; mean of a probe "
+                   "before and a probe after the e2e segments",
             # the same copies as the e2e path issues (slice size, slices per
             # step, each download behind its upload, two buffer sets), without
             # the library and without kernels

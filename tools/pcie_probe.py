@@ -28,10 +28,18 @@ def _check(res):
     return rest[0] if len(rest) == 1 else rest
 
 
-def measure(device, mib=256, reps=6, barrier=None, write_combined=False):
+def measure(device, mib=256, reps=6, barrier=None, write_combined=False,
+            seconds=None):
     """GB/s of pinned-host <-> device copies on `device`: h2d alone, d2h alone,
     both at once (per direction).  `barrier()` (optional) is called right before
-    each timed region so that several ranks copy concurrently."""
+    each timed region so that several ranks copy concurrently.
+
+    `seconds` (None: `reps` copies): copy for that long instead of a fixed
+    number of times.  With several ranks a fixed amount of work flatters the
+    aggregate -- the GPUs with the larger share of the host fabric finish early
+    and the others then speed up -- while a fixed time keeps every rank copying
+    against all the others for the whole measurement: the steady-state figure,
+    which is what a job that keeps all GPUs busy can get."""
     from cuda.bindings import runtime as rt
     _check(rt.cudaSetDevice(device))
     nbytes = mib * MIB
@@ -61,6 +69,20 @@ def measure(device, mib=256, reps=6, barrier=None, write_combined=False):
         _check(rt.cudaDeviceSynchronize())
         if barrier is not None:
             barrier()
+        if seconds is not None:
+            # one copy (pair) at a time until the time is up; both directions
+            # of a pair run concurrently and the pair ends with the slower one
+            import time
+            t0 = time.perf_counter()
+            done = 0
+            while True:
+                once(up, down)
+                _check(rt.cudaStreamSynchronize(s_up))
+                _check(rt.cudaStreamSynchronize(s_down))
+                done += 1
+                elapsed = time.perf_counter() - t0
+                if elapsed >= seconds:
+                    return nbytes * done / elapsed / 1e9
         # both streams start behind e0; e1 follows the end of both
         _check(rt.cudaEventRecord(e0, s_up))
         _check(rt.cudaStreamWaitEvent(s_down, e0, 0))
@@ -91,14 +113,16 @@ def measure(device, mib=256, reps=6, barrier=None, write_combined=False):
     return out
 
 
-def measure_pipelined(device, chunk_bytes, chunks=4, steps=20, barrier=None):
+def measure_pipelined(device, chunk_bytes, chunks=4, steps=20, barrier=None,
+                      seconds=None):
     """GB/s per direction of the copy pattern of bench.py's e2e path WITHOUT
     the library and without kernels: per step `chunks` slices of `chunk_bytes`,
     each uploaded into its own device buffer and downloaded again as soon as
     its upload has ended; two sets of device buffers used alternately, an
     upload into a buffer waits for the download that last read it.  The figure
     a pipeline with these dependencies can reach, as opposed to two independent
-    streams of 128 MiB copies (measure)."""
+    streams of 128 MiB copies (measure).  `seconds`: steps for that long
+    instead of `steps` of them (see measure)."""
     from cuda.bindings import runtime as rt
     _check(rt.cudaSetDevice(device))
     total = chunk_bytes * chunks
@@ -136,8 +160,24 @@ def measure_pipelined(device, chunk_bytes, chunks=4, steps=20, barrier=None):
         barrier()
     _check(rt.cudaEventRecord(e0, s_up))
     _check(rt.cudaStreamWaitEvent(s_down, e0, 0))
-    for k in range(steps):
-        step(k, False)
+    if seconds is None:
+        for k in range(steps):
+            step(k, False)
+    else:
+        # keep two steps enqueued (as the double-buffered e2e loop does) and
+        # stop when the time is up
+        import time
+        t0 = time.perf_counter()
+        steps = 0
+        while True:
+            step(steps, False)
+            steps += 1
+            if steps >= 2:
+                # wait for the step before the one just enqueued
+                _check(rt.cudaEventSynchronize(
+                    down_done[(steps - 2) & 1][chunks - 1]))
+                if time.perf_counter() - t0 >= seconds:
+                    break
     _check(rt.cudaEventRecord(ej, s_down))
     _check(rt.cudaStreamWaitEvent(s_up, ej, 0))
     _check(rt.cudaEventRecord(e1, s_up))
@@ -178,11 +218,14 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("gloo")
         barrier = dist.barrier
-    mine = measure(local_rank, barrier=barrier, write_combined=wc)
+    secs = 0.4 if world > 1 else None
+    mine = measure(local_rank, barrier=barrier, write_combined=wc,
+                   mib=32 if secs else 256, seconds=secs)
     # the e2e path's slices at this number of GPUs (bench.py: 32/world limbs x
     # 4 batch entries of 512 KiB per slice, 4 slices per step)
     mine.update(measure_pipelined(local_rank, (32 // world) * 4 * 512 * 1024,
-                                  barrier=barrier))
+                                  barrier=barrier, seconds=secs))
+    mine["seconds_per_measurement"] = secs
     if dist is not None:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
