@@ -20,8 +20,12 @@ key `weak`.
 One JSON line is printed by rank 0.  `value` is measured with the inputs
 resident in HBM; `e2e` is the same metric through the C-ABI with host buffers
 (pinned host -> device copy of the step's input and device -> host copy of its
-result inside the timed region) next to `e2e_ceiling`, the box's own host <->
-device bandwidth measured in the same run without the library.  `roofline`
+result inside the timed region; median of three segments) next to
+`e2e_ceiling`, the box's own host <-> device bandwidth measured without the
+library right before and right after those segments.  At N > 1 the end-to-end
+path shards by the per-GPU rates it has just measured (vkhel_b200/shard.py,
+e2e_plan): the GPUs of a box do not get equal shares of the host fabric, and
+with equal shards the job would end with the slowest one.  `roofline`
 places the step against the HBM roofline with the algorithmic 16*n bytes per
 NTT; `issue_roofline` against the integer (fmaheavy) pipe, with the pipe rates
 and the register-only butterfly rate measured in this run
