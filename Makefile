@@ -67,7 +67,8 @@ $(STATIC): $(OBJS)
 $(SHARED): $(OBJS) vkhel.syms
 	@mkdir -p $(LIB_DIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) \
-		-Xlinker --version-script=vkhel.syms -Xlinker -soname=libvkhel.so
+		-Xlinker --version-script=vkhel.syms -Xlinker -soname=libvkhel.so \
+		-Xlinker -z -Xlinker nodelete
 
 # ---- the reference's own programs, compiled from where they lie, unmodified ----
 # (include path = include/ and include/vkhel/, as in meson.build:31-32)

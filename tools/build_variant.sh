@@ -15,5 +15,5 @@ for f in numbers ntt_tables; do
   /usr/bin/gcc -O2 -fPIC -Iinclude -Iinclude/vkhel -c vkhel_b200/csrc/$f.c -o $out/obj_$name/$f.o
 done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libvkhel_$name.so \
-  $out/obj_$name/*.o -Xlinker --version-script=vkhel.syms
+  $out/obj_$name/*.o -Xlinker --version-script=vkhel.syms -Xlinker -z -Xlinker nodelete
 echo built $out/libvkhel_$name.so

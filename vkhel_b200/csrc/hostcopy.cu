@@ -16,13 +16,18 @@
  * variable.  One job at a time: a caller that finds the pool taken (another
  * thread of the application is inside a copy) copies on its own.
  * $VKHEL_COPY_THREADS sets the number of threads per copy including the
- * caller (default 3, 1 = plain memcpy, at most 8).
+ * caller (default 3, 1 = plain memcpy, at most 8; never more than the CPUs the
+ * process is allowed on).  The helpers block every signal, and libvkhel.so is
+ * linked with -z nodelete: a dlclose() must not unmap code they are running.
  */
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
 
+#include <pthread.h>
+#include <sched.h>
+#include <signal.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -100,6 +105,10 @@ void take_parts(copy_pool *p, uint64_t gen) {
 }
 
 void helper_main(copy_pool *p) {
+	/* signals are the application's business: none is handled here */
+	sigset_t all;
+	sigfillset(&all);
+	pthread_sigmask(SIG_BLOCK, &all, NULL);
 	uint64_t seen = 0;   /* generation of the last job worked on */
 	for (;;) {
 		const uint64_t idle_since = now_ns();
@@ -136,9 +145,15 @@ extern "C" void host_copy(void *dst, const void *src, size_t bytes) {
 	if (g_threads < 0) {
 		const char *env = getenv("VKHEL_COPY_THREADS");
 		int n = env && *env ? atoi(env) : 3;
-		const unsigned hw = std::thread::hardware_concurrency();
-		if (hw && (unsigned) n > hw) {
-			n = (int) hw;
+		/* no more threads than CPUs this process may run on (a caller pinned
+		 * to one core gets the plain memcpy) */
+		cpu_set_t cpus;
+		int allowed = (int) std::thread::hardware_concurrency();
+		if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0) {
+			allowed = CPU_COUNT(&cpus);
+		}
+		if (allowed > 0 && n > allowed) {
+			n = allowed;
 		}
 		g_threads = n < 1 ? 1 : n > COPY_MAX_THREADS ? COPY_MAX_THREADS : n;
 	}
