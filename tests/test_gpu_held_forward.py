@@ -143,6 +143,26 @@ def test_held_forward_read_by_anything_else_is_canonical(own_ctx):
     first = want[:basis.n]
     assert np.array_equal(d.to_host(), oracle.forward(first, basis.ora[0]))
     assert np.array_equal(b.to_host(), want)
+
+    # ... and the matching inverse arrives while that transform is still only
+    # recorded: it must read the canonical result, whatever its modulus
+    foreign = vk.NttTables(basis.n, other.qs[0],
+                           params.find_psi(basis.n, other.qs[0]), ctx=ctx)
+    lazy = held_forward()
+    ctx.forward_transform(b, d, foreign)
+    ctx.inverse_transform_rns(b, b, basis.lib, batch)
+    assert ctx.lazy_forwards == lazy
+    assert np.array_equal(d.to_host(), oracle.forward(first, other.ora[0]))
+    assert np.array_equal(b.to_host(), x)
+    # the same with a recorded point-wise product of the result
+    lazy = held_forward()
+    e = ctx.vector(basis.n)
+    ctx.elemmul(b, b, e, other.qs[0])
+    ctx.inverse_transform_rns(b, b, basis.lib, batch)
+    assert ctx.lazy_forwards == lazy
+    assert np.array_equal(e.to_host(), oracle.elemmul(first, first, other.qs[0]))
+    assert np.array_equal(b.to_host(), x)
+    e.destroy(), foreign.destroy()
     for v in (a, b, c, d):
         v.destroy()
     single.destroy(), basis.destroy(), other.destroy()

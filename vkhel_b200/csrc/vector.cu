@@ -520,7 +520,12 @@ static void inverse_follows(const struct vkhel_vector *operand,
 	held_forward &h = dq->fwd;
 	const bool in_place = operand == result;
 	if (h.active) {
-		if (in_place && h.result == result && h.descs == descs
+		/* nothing may have been recorded since the forward transform was held:
+		 * a recorded operation could read its result, and would be launched
+		 * between the lazy forward and this inverse */
+		const bool quiet = dq->items.empty() && dq->products.empty()
+			&& dq->inv_products.empty() && !dq->mul.active && !dq->triple.active;
+		if (quiet && in_place && h.result == result && h.descs == descs
 				&& h.polys == polys) {
 			launch_held_forward(result->ctx, dq, true);
 		}
