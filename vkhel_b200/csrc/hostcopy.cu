@@ -61,7 +61,6 @@ struct copy_pool {
 
 copy_pool *g_pool;   /* never freed: the helpers outlive static destructors */
 std::once_flag g_pool_once;
-int g_threads = -1;
 
 uint64_t now_ns() {
 	struct timespec ts;
@@ -132,17 +131,10 @@ void helper_main(copy_pool *p) {
 	}
 }
 
-void pool_start() {
-	g_pool = new copy_pool;
-	for (int i = 0; i + 1 < g_threads; i++) {
-		std::thread(helper_main, g_pool).detach();
-	}
-}
-
-}  // namespace
-
-extern "C" void host_copy(void *dst, const void *src, size_t bytes) {
-	if (g_threads < 0) {
+/* threads per copy, the caller included: read once, whichever application
+ * thread comes first */
+int copy_threads() {
+	static const int threads = [] {
 		const char *env = getenv("VKHEL_COPY_THREADS");
 		int n = env && *env ? atoi(env) : 3;
 		/* no more threads than CPUs this process may run on (a caller pinned
@@ -155,9 +147,23 @@ extern "C" void host_copy(void *dst, const void *src, size_t bytes) {
 		if (allowed > 0 && n > allowed) {
 			n = allowed;
 		}
-		g_threads = n < 1 ? 1 : n > COPY_MAX_THREADS ? COPY_MAX_THREADS : n;
+		return n < 1 ? 1 : n > COPY_MAX_THREADS ? COPY_MAX_THREADS : n;
+	}();
+	return threads;
+}
+
+void pool_start() {
+	g_pool = new copy_pool;
+	for (int i = 0; i + 1 < copy_threads(); i++) {
+		std::thread(helper_main, g_pool).detach();
 	}
-	if (g_threads == 1 || bytes < COPY_MIN_BYTES) {
+}
+
+}  // namespace
+
+extern "C" void host_copy(void *dst, const void *src, size_t bytes) {
+	const int threads = copy_threads();
+	if (threads == 1 || bytes < COPY_MIN_BYTES) {
 		memcpy(dst, src, bytes);
 		return;
 	}
