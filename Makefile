@@ -108,7 +108,11 @@ $(BIN_DIR)/vulkan_dump: tools/vulkan_dump.c $(SHARED)
 	$(HOSTCC) -O2 -Wall $(INC) $< -o $@ -L$(LIB_DIR) -lvkhel -Wl,-rpath,'$$ORIGIN/../../$(LIB_DIR)'
 
 # micro-benchmarks behind the roofline denominators (profiles/*bench*.txt)
-tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench $(BIN_DIR)/exchange_bench
+tools: $(BIN_DIR)/pipe_bench $(BIN_DIR)/bfly_bench $(BIN_DIR)/exchange_bench \
+       $(BIN_DIR)/hostcopy_bench
+$(BIN_DIR)/hostcopy_bench: tools/hostcopy_bench.cpp $(OBJ_DIR)/hostcopy.o
+	@mkdir -p $(BIN_DIR)
+	g++ -O2 $^ -o $@ $(CUDA_LIBS)
 $(BIN_DIR)/%_bench: tools/%_bench.cu
 	@mkdir -p $(BIN_DIR)
 	$(NVCC) $(ARCH) -O3 -o $@ $<

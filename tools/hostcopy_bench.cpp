@@ -1,3 +1,5 @@
+// 64 copies of 512 KiB through host_copy (vkhel_b200/csrc/hostcopy.cu), the staging copy of
+// vkhel_vector_copy_from_host, alone: make build/bin/hostcopy_bench; VKHEL_COPY_THREADS=1..8 build/bin/hostcopy_bench
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
